@@ -1,0 +1,935 @@
+// libvcb200.so -- engine object + C ABI of the codec-LM decode path (include/vcb200.h).
+//
+// Owns: bf16 GEMM weights + their TMA descriptors, fp32 embeddings / LayerNorm / biases, the paged KV pool,
+// per-slot / per-group device state, step workspaces.  The caller (Python/torch) owns inputs, outputs and the stream.
+#include "../../include/vcb200.h"
+#include "lm_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+namespace vcb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __float2bfloat16_rn(in[i]);
+}
+
+struct Matrix {                 // bf16 GEMM operand + descriptor
+    __nv_bfloat16* w = nullptr;
+    int rows = 0, cols = 0;
+    CUtensorMap tm;
+};
+
+struct Layer {
+    Matrix qkv, out, ff1, ff2;
+    float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    float *b_qkv = nullptr, *b_out = nullptr, *b_ff1 = nullptr, *b_ff2 = nullptr;
+    void *kpool = nullptr, *vpool = nullptr;
+};
+
+}  // namespace vcb
+
+using namespace vcb;
+
+struct vcb_engine {
+    vcb_config cfg;
+    ModelDims m;
+    int num_sms = 148;
+    int kv_fp32 = 0;
+    int max_pages_per_slot = 0, n_pages = 0;
+    std::vector<int> free_pages;
+    std::vector<std::vector<int>> slot_pages;
+    std::vector<int> slot_group;      // host mirror: group id per slot (-1 closed)
+    std::vector<int> free_groups;
+
+    std::map<std::string, float*> f32;            // every loaded fp32 tensor (device)
+    std::map<std::string, std::vector<int64_t>> shapes;
+    std::vector<Layer> layers;
+    Matrix h1;                                    // stacked predict_layer.{k}.0  [K*Hh, d]
+    std::vector<Matrix> h2;                       // predict_layer.{k}.2  [V, Hh]
+    float *b_h1 = nullptr;                        // [K*Hh]
+    float **d_bias2 = nullptr;                    // device array of K pointers
+    float **d_E_audio = nullptr;                  // device array of K pointers
+    float *E_text = nullptr, *mask_emb = nullptr, *pe = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+    float alpha_t = 1.f, alpha_a = 1.f;
+    bool finalized = false;
+
+    // workspaces
+    static constexpr int MAX_ROWS = 128;
+    float *x_rows = nullptr, *qbuf = nullptr, *partial = nullptr, *x_slot = nullptr, *h_slot = nullptr;
+    __nv_bfloat16 *act_d = nullptr, *act_f = nullptr, *act_h = nullptr;
+    CUtensorMap tm_act_d[4], tm_act_f[4], tm_act_h[4];   // bpad = 16, 32, 64, 128
+    size_t partial_floats = 0;
+    int *row_slot = nullptr, *row_pos = nullptr, *row_last = nullptr, *page_table = nullptr;   // decode-step rows
+    int *all_rows = nullptr;          // prefill row tables: 4 arrays of all_rows_cap ints (seq, pos, slot, last)
+    size_t all_rows_cap = 0;
+    const int *cur_slot = nullptr, *cur_pos = nullptr, *cur_last = nullptr;   // tables used by forward_rows
+    int *d_slots = nullptr;
+    std::vector<int> last_slots;      // host mirror of d_slots (skip re-upload when unchanged)
+    int *tok_log = nullptr;
+    float *dbg_logits = nullptr;
+    SlotState* st = nullptr;
+    GroupState* gr = nullptr;
+    EmbedSeq* d_seqs = nullptr;
+    // pinned staging
+    int* h_stage = nullptr;
+    size_t h_stage_ints = 0;
+    cudaEvent_t stage_ev = nullptr;
+
+    int opt_simt = 0, opt_pdl = 0;
+    int64_t n_launches = 0;
+};
+
+namespace {
+
+int bpad_for(int rows) { return rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : 128; }
+int bpad_idx(int bpad) { return bpad == 16 ? 0 : bpad == 32 ? 1 : bpad == 64 ? 2 : 3; }
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    VCB_CUDA_OK(cudaMemset(*p, 0, n * sizeof(T)));
+    return 0;
+}
+
+int to_bf16_matrix(vcb_engine* e, const std::string& key, Matrix* M, int rows, int cols) {
+    auto it = e->f32.find(key);
+    if (it == e->f32.end()) {
+        set_error("missing weight %s", key.c_str());
+        return -1;
+    }
+    const auto& sh = e->shapes[key];
+    if (sh.size() != 2 || sh[0] != rows || sh[1] != cols) {
+        set_error("weight %s has wrong shape", key.c_str());
+        return -1;
+    }
+    const size_t n = static_cast<size_t>(rows) * cols;
+    if (!M->w) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&M->w), n * 2));
+    f32_to_bf16_kernel<<<1024, 256>>>(it->second, M->w, n);
+    VCB_CUDA_OK(cudaGetLastError());
+    M->rows = rows;
+    M->cols = cols;
+    return make_tmap_bf16_2d(&M->tm, M->w, rows, cols, cols, 128);
+}
+
+int need(vcb_engine* e, const std::string& key, float** out, size_t numel) {
+    auto it = e->f32.find(key);
+    if (it == e->f32.end()) {
+        set_error("missing weight %s", key.c_str());
+        return -1;
+    }
+    size_t n = 1;
+    for (auto s : e->shapes[key]) n *= static_cast<size_t>(s);
+    if (n != numel) {
+        set_error("weight %s: expected %zu elements, got %zu", key.c_str(), numel, n);
+        return -1;
+    }
+    *out = it->second;
+    return 0;
+}
+
+int free_weight_f32(vcb_engine* e, const std::string& key) {   // bf16 copy made: drop the fp32 staging copy
+    auto it = e->f32.find(key);
+    if (it != e->f32.end()) {
+        cudaFree(it->second);
+        e->f32.erase(it);
+    }
+    return 0;
+}
+
+// stage a small int array to the device (pinned ring; serialised by an event so the buffer is never overwritten early)
+int upload_ints(vcb_engine* e, const int* src, size_t n, int* dst, cudaStream_t st) {
+    if (n > e->h_stage_ints) {
+        set_error("staging overflow");
+        return -1;
+    }
+    VCB_CUDA_OK(cudaEventSynchronize(e->stage_ev));
+    memcpy(e->h_stage, src, n * sizeof(int));
+    VCB_CUDA_OK(cudaMemcpyAsync(dst, e->h_stage, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    VCB_CUDA_OK(cudaEventRecord(e->stage_ev, st));
+    return 0;
+}
+
+#define LAUNCH_COUNT(e) ((e)->n_launches++)
+
+int run_gemm(vcb_engine* e, const Matrix& W, const CUtensorMap* tmB, const __nv_bfloat16* X, int ldx, int bpad,
+             int nvalid, int b_col_off, int kdim, int* splits_out, cudaStream_t st) {
+    GemmCall g;
+    g.tmA = &W.tm;
+    g.tmB = tmB;
+    g.W = W.w;
+    g.X = X;
+    g.partial = e->partial;
+    g.Nout = W.rows;
+    g.Kdim = kdim;
+    g.ldx = ldx;
+    g.ldp = (W.rows + 3) & ~3;
+    g.bpad = bpad;
+    g.splits = gemm_pick_splits(W.rows, kdim, e->num_sms);
+    g.b_col_off = b_col_off;
+    g.nvalid = nvalid;
+    g.pdl = e->opt_pdl;
+    g.simt = e->opt_simt;
+    if (static_cast<size_t>(g.splits) * bpad * g.ldp > e->partial_floats) {
+        set_error("partial workspace too small");
+        return -1;
+    }
+    *splits_out = g.splits;
+    LAUNCH_COUNT(e);
+    return gemm_launch(g, st);
+}
+
+template <typename KVT>
+int launch_attn_t(vcb_engine* e, const Layer& Ly, int rows, int bpad, cudaStream_t st) {
+    const ModelDims& m = e->m;
+    const float scale = 1.0f / sqrtf(static_cast<float>(m.hd));
+    if (m.hd == 128) {
+        using L = AttSmem<KVT, 128>;
+        static bool set = false;
+        if (!set) {
+            VCB_CUDA_OK(cudaFuncSetAttribute(attn_rows_kernel<KVT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             L::TOTAL));
+            set = true;
+        }
+        attn_rows_kernel<KVT, 128><<<rows * m.H, ATT_THREADS, L::TOTAL, st>>>(
+            e->qbuf, static_cast<const KVT*>(Ly.kpool), static_cast<const KVT*>(Ly.vpool), e->page_table,
+            e->max_pages_per_slot, e->cur_slot, e->cur_pos, m.H, e->act_d, m.d, bpad, scale);
+    } else {
+        using L = AttSmem<KVT, 64>;
+        static bool set = false;
+        if (!set) {
+            VCB_CUDA_OK(cudaFuncSetAttribute(attn_rows_kernel<KVT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             L::TOTAL));
+            set = true;
+        }
+        attn_rows_kernel<KVT, 64><<<rows * m.H, ATT_THREADS, L::TOTAL, st>>>(
+            e->qbuf, static_cast<const KVT*>(Ly.kpool), static_cast<const KVT*>(Ly.vpool), e->page_table,
+            e->max_pages_per_slot, e->cur_slot, e->cur_pos, m.H, e->act_d, m.d, bpad, scale);
+    }
+    VCB_CUDA_OK(cudaGetLastError());
+    LAUNCH_COUNT(e);
+    return 0;
+}
+
+int launch_ln(vcb_engine* e, const float* x_in, const int* src_index, float* x_out, int nsplit, int ldp, int bpad,
+              const float* bias, const float* g, const float* b, int rows, cudaStream_t st) {
+    const int d = e->m.d;
+    if (d <= 2048)
+        ln_rows_kernel<8><<<rows, 256, 0, st>>>(x_in, src_index, x_out, e->partial, nsplit, ldp, bpad, bias, g, b,
+                                                 e->act_d, d, d, 1e-5f);
+    else
+        ln_rows_kernel<16><<<rows, 256, 0, st>>>(x_in, src_index, x_out, e->partial, nsplit, ldp, bpad, bias, g, b,
+                                                  e->act_d, d, d, 1e-5f);
+    VCB_CUDA_OK(cudaGetLastError());
+    LAUNCH_COUNT(e);
+    return 0;
+}
+
+// All transformer layers over `rows` rows whose embeddings are in x_rows and (slot,pos) in row_slot/row_pos.
+// Leaves the final hidden state of rows flagged in row_last in h_slot.   (transformer.py:473-488)
+int forward_rows(vcb_engine* e, int rows, cudaStream_t st) {
+    const ModelDims& m = e->m;
+    const int bpad = bpad_for(rows);
+    const int bi = bpad_idx(bpad);
+    int sp_prev = 0, ldp_prev = 0;
+    const float* bias_prev = nullptr;
+    for (int l = 0; l < m.L; ++l) {
+        const Layer& Ly = e->layers[l];
+        // LN1 (+ residual / split-K reduce of the previous layer's FFN2)
+        if (launch_ln(e, e->x_rows, nullptr, l == 0 ? nullptr : e->x_rows, sp_prev, ldp_prev, bpad, bias_prev, Ly.ln1_g,
+                      Ly.ln1_b, rows, st))
+            return -1;
+        int sp;
+        if (run_gemm(e, Ly.qkv, &e->tm_act_d[bi], e->act_d, m.d, bpad, rows, 0, m.d, &sp, st)) return -1;
+        const int ldp_qkv = (3 * m.d + 3) & ~3;
+        if (e->kv_fp32)
+            qkv_finish_kernel<float><<<rows, 256, 0, st>>>(e->partial, sp, ldp_qkv, bpad, Ly.b_qkv, e->qbuf,
+                                                          static_cast<float*>(Ly.kpool), static_cast<float*>(Ly.vpool),
+                                                          e->page_table, e->max_pages_per_slot, e->cur_slot, e->cur_pos,
+                                                          m.d, m.H, m.hd);
+        else
+            qkv_finish_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(
+                e->partial, sp, ldp_qkv, bpad, Ly.b_qkv, e->qbuf, static_cast<__nv_bfloat16*>(Ly.kpool),
+                static_cast<__nv_bfloat16*>(Ly.vpool), e->page_table, e->max_pages_per_slot, e->cur_slot, e->cur_pos,
+                m.d, m.H, m.hd);
+        VCB_CUDA_OK(cudaGetLastError());
+        LAUNCH_COUNT(e);
+        if (e->kv_fp32 ? launch_attn_t<float>(e, Ly, rows, bpad, st) : launch_attn_t<__nv_bfloat16>(e, Ly, rows, bpad, st))
+            return -1;
+        if (run_gemm(e, Ly.out, &e->tm_act_d[bi], e->act_d, m.d, bpad, rows, 0, m.d, &sp, st)) return -1;
+        // x += attn + b_out ; LN2
+        if (launch_ln(e, e->x_rows, nullptr, e->x_rows, sp, (m.d + 3) & ~3, bpad, Ly.b_out, Ly.ln2_g, Ly.ln2_b, rows, st))
+            return -1;
+        if (run_gemm(e, Ly.ff1, &e->tm_act_d[bi], e->act_d, m.d, bpad, rows, 0, m.d, &sp, st)) return -1;
+        bias_act_kernel<<<dim3((m.F + 255) / 256, rows), 256, 0, st>>>(e->partial, sp, (m.F + 3) & ~3, bpad, Ly.b_ff1,
+                                                                       m.F, 1, e->act_f, m.F);
+        VCB_CUDA_OK(cudaGetLastError());
+        LAUNCH_COUNT(e);
+        if (run_gemm(e, Ly.ff2, &e->tm_act_f[bi], e->act_f, m.F, bpad, rows, 0, m.F, &sp, st)) return -1;
+        sp_prev = sp;
+        ldp_prev = (m.d + 3) & ~3;
+        bias_prev = Ly.b_ff2;
+    }
+    reduce_rows_kernel<<<rows, 256, 0, st>>>(e->x_rows, e->partial, sp_prev, ldp_prev, bpad, bias_prev, e->h_slot,
+                                             e->cur_last, m.d);
+    VCB_CUDA_OK(cudaGetLastError());
+    LAUNCH_COUNT(e);
+    return 0;
+}
+
+int upload_slots(vcb_engine* e, const int32_t* slots, int n, cudaStream_t st) {
+    if (n < 1 || n > vcb_engine::MAX_ROWS || n > e->cfg.max_slots) {
+        set_error("bad slot count %d", n);
+        return -1;
+    }
+    for (int i = 0; i < n; ++i)
+        if (slots[i] < 0 || slots[i] >= e->cfg.max_slots || e->slot_group[slots[i]] < 0) {
+            set_error("slot %d is not open", slots[i]);
+            return -1;
+        }
+    if (static_cast<int>(e->last_slots.size()) == n && std::equal(slots, slots + n, e->last_slots.begin())) return 0;
+    e->last_slots.assign(slots, slots + n);
+    return upload_ints(e, slots, n, e->d_slots, st);
+}
+
+// final LayerNorm + logit heads + fused sampler for the n listed slots (d_slots already uploaded)
+int sample_rows(vcb_engine* e, int n, const float* noise, const vcb_sampling* sp, cudaStream_t st) {
+    const ModelDims& m = e->m;
+    const int bpad = bpad_for(n), bi = bpad_idx(bpad);
+    if (launch_ln(e, e->h_slot, e->d_slots, nullptr, 0, 0, bpad, nullptr, e->lnf_g, e->lnf_b, n, st)) return -1;
+    int s1;
+    if (run_gemm(e, e->h1, &e->tm_act_d[bi], e->act_d, m.d, bpad, n, 0, m.d, &s1, st)) return -1;
+    const int KH = m.K * m.Hh;
+    bias_act_kernel<<<dim3((KH + 255) / 256, n), 256, 0, st>>>(e->partial, s1, (KH + 3) & ~3, bpad, e->b_h1, KH, 2,
+                                                               e->act_h, KH);
+    VCB_CUDA_OK(cudaGetLastError());
+    LAUNCH_COUNT(e);
+    // K second-stage GEMMs write disjoint column blocks [k*Vpad, (k+1)*Vpad) of one logits partial buffer
+    const int ldp = m.K * m.Vpad;
+    const int s2 = gemm_pick_splits(m.V, m.Hh, e->num_sms);
+    if (static_cast<size_t>(s2) * bpad * ldp > e->partial_floats) {
+        set_error("partial workspace too small for logits");
+        return -1;
+    }
+    // the logits partials live in the upper half of the workspace so GEMM1's partials (still being read) are untouched
+    float* lp = e->partial + e->partial_floats;
+    for (int k = 0; k < m.K; ++k) {
+        GemmCall g;
+        g.tmA = &e->h2[k].tm;
+        g.tmB = &e->tm_act_h[bi];
+        g.W = e->h2[k].w;
+        g.X = e->act_h;
+        g.partial = lp + k * m.Vpad;
+        g.Nout = m.V;
+        g.Kdim = m.Hh;
+        g.ldx = KH;
+        g.ldp = ldp;
+        g.bpad = bpad;
+        g.splits = s2;
+        g.b_col_off = k * m.Hh;
+        g.nvalid = n;
+        g.pdl = e->opt_pdl;
+        g.simt = e->opt_simt;
+        LAUNCH_COUNT(e);
+        if (gemm_launch(g, st)) return -1;
+    }
+    SamplerArgs a;
+    a.slots = e->d_slots;
+    a.n = n;
+    a.st = e->st;
+    a.gr = e->gr;
+    a.partial = lp;
+    a.nsplit = s2;
+    a.ldp = ldp;
+    a.bpad = bpad;
+    a.bias2 = e->d_bias2;
+    a.noise = noise;
+    a.dbg_logits = e->dbg_logits;
+    a.tok_log = e->tok_log;
+    a.max_steps = e->cfg.max_new_tokens;
+    a.x_slot = e->x_slot;
+    a.E_audio = e->d_E_audio;
+    a.mask_emb = e->mask_emb;
+    a.pe = e->pe;
+    a.alpha_a = e->alpha_a;
+    a.d = m.d;
+    a.K = m.K;
+    a.V = m.V;
+    a.Vpad = m.Vpad;
+    a.empty_token = m.empty_token;
+    a.eog = m.eog;
+    a.eos = m.eos;
+    a.encodec_sr = m.encodec_sr;
+    a.sp.top_k = sp->top_k;
+    a.sp.top_p = sp->top_p;
+    a.sp.temperature = sp->temperature;
+    a.sp.stop_repetition = sp->stop_repetition;
+    a.sp.n_silence = std::min(sp->n_silence, 8);
+    for (int i = 0; i < 8; ++i) a.sp.silence_tokens[i] = sp->silence_tokens[i];
+    const size_t dyn = SAMP_SORT_N * 8 + static_cast<size_t>(m.V) * 4;
+    sampler_kernel<<<n * m.K, SAMP_THREADS, dyn, st>>>(a);
+    VCB_CUDA_OK(cudaGetLastError());
+    LAUNCH_COUNT(e);
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* vcb_last_error(void) { return get_error(); }
+int vcb_version(void) { return 100; }
+
+int vcb_create(const vcb_config* cfg, vcb_engine** out) {
+    if (!cfg || !out) {
+        set_error("null argument");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libvcb200 has no CPU fallback");
+        return -2;
+    }
+    VCB_CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    VCB_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error("libvcb200 is built for sm_100a only; device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+        return -2;
+    }
+    vcb_engine* e = new vcb_engine();
+    e->cfg = *cfg;
+    e->num_sms = prop.multiProcessorCount;
+    ModelDims& m = e->m;
+    m.d = cfg->d_model;
+    m.H = cfg->nhead;
+    m.hd = m.d / m.H;
+    m.L = cfg->num_layers;
+    m.F = 4 * m.d;
+    m.K = cfg->n_codebooks;
+    m.V = cfg->audio_vocab_size + cfg->n_special;
+    m.Vpad = (m.V + 3) & ~3;
+    m.Hh = cfg->audio_vocab_size / 2;
+    m.n_text = cfg->text_vocab_rows;
+    m.empty_token = cfg->empty_token;
+    m.eog = cfg->eog;
+    m.eos = cfg->eos > 0 ? cfg->eos : -1;
+    m.audio_pad = cfg->audio_pad_token;
+    m.encodec_sr = cfg->encodec_sr;
+    m.max_n_spans = cfg->max_n_spans;
+    if ((m.hd != 128 && m.hd != 64) || m.d % 64 || m.Hh % 64 || m.d > 4096 || m.V > SAMP_MAXV * SAMP_THREADS ||
+        m.K < 1 || m.K > 8) {
+        set_error("unsupported shape: d=%d H=%d hd=%d Hh=%d V=%d K=%d", m.d, m.H, m.hd, m.Hh, m.V, m.K);
+        delete e;
+        return -1;
+    }
+    e->kv_fp32 = cfg->kv_dtype == VCB_KV_FP32;
+    e->max_pages_per_slot = (cfg->max_seq_len + KV_PAGE - 1) / KV_PAGE;
+    e->n_pages = e->max_pages_per_slot * cfg->max_slots;
+    for (int p = e->n_pages - 1; p >= 0; --p) e->free_pages.push_back(p);
+    e->slot_pages.resize(cfg->max_slots);
+    e->slot_group.assign(cfg->max_slots, -1);
+    for (int g = cfg->max_slots - 1; g >= 0; --g) e->free_groups.push_back(g);
+    e->layers.resize(m.L);
+    e->h2.resize(m.K);
+    const char* simt = getenv("VCB_GEMM_IMPL");
+    e->opt_simt = simt && !strcmp(simt, "simt");
+    *out = e;
+    return 0;
+}
+
+int vcb_destroy(vcb_engine* e) {
+    if (!e) return 0;
+    cudaDeviceSynchronize();
+    for (auto& kv : e->f32) cudaFree(kv.second);
+    for (auto& L : e->layers) {
+        cudaFree(L.qkv.w); cudaFree(L.out.w); cudaFree(L.ff1.w); cudaFree(L.ff2.w);
+        cudaFree(L.kpool); cudaFree(L.vpool);
+    }
+    cudaFree(e->h1.w);
+    for (auto& M : e->h2) cudaFree(M.w);
+    void* ptrs[] = {e->b_h1, e->d_bias2, e->d_E_audio, e->pe, e->x_rows, e->qbuf, e->partial, e->x_slot, e->h_slot,
+                    e->act_d, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->all_rows, e->page_table,
+                    e->d_slots, e->tok_log, e->dbg_logits, e->st, e->gr, e->d_seqs};
+    for (void* p : ptrs) cudaFree(p);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->stage_ev) cudaEventDestroy(e->stage_ev);
+    delete e;
+    return 0;
+}
+
+int vcb_load_weight(vcb_engine* e, const char* key, const float* data, const int64_t* shape, int32_t ndim,
+                    int32_t is_device_ptr) {
+    if (!e || !key || !data) {
+        set_error("null argument");
+        return -1;
+    }
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    size_t n = 1;
+    std::vector<int64_t> sh(shape, shape + ndim);
+    for (auto s : sh) n *= static_cast<size_t>(s);
+    float* dptr = nullptr;
+    auto it = e->f32.find(key);
+    if (it != e->f32.end()) {
+        cudaFree(it->second);
+        e->f32.erase(it);
+    }
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dptr), std::max<size_t>(n, 1) * sizeof(float)));
+    VCB_CUDA_OK(cudaMemcpy(dptr, data, n * sizeof(float), is_device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    e->f32[key] = dptr;
+    e->shapes[key] = sh;
+    e->finalized = false;
+    return 0;
+}
+
+int vcb_load_pe(vcb_engine* e, const float* data, int32_t rows, int32_t is_device_ptr) {
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    if (e->pe) cudaFree(e->pe);
+    const size_t n = static_cast<size_t>(rows) * e->m.d;
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->pe), n * sizeof(float)));
+    VCB_CUDA_OK(cudaMemcpy(e->pe, data, n * sizeof(float), is_device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    e->m.pe_len = rows;
+    return 0;
+}
+
+int vcb_finalize_weights(vcb_engine* e) {
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    const ModelDims& m = e->m;
+    if (!e->pe || m.pe_len < e->cfg.max_seq_len) {
+        set_error("positional table missing or shorter than max_seq_len");
+        return -1;
+    }
+    char key[256];
+    for (int l = 0; l < m.L; ++l) {
+        Layer& L = e->layers[l];
+        auto K = [&](const char* suffix) {
+            snprintf(key, sizeof(key), "decoder.layers.%d.%s", l, suffix);
+            return std::string(key);
+        };
+        if (to_bf16_matrix(e, K("self_attn.in_proj_weight"), &L.qkv, 3 * m.d, m.d)) return -1;
+        if (to_bf16_matrix(e, K("self_attn.out_proj.weight"), &L.out, m.d, m.d)) return -1;
+        if (to_bf16_matrix(e, K("linear1.weight"), &L.ff1, m.F, m.d)) return -1;
+        if (to_bf16_matrix(e, K("linear2.weight"), &L.ff2, m.d, m.F)) return -1;
+        if (need(e, K("self_attn.in_proj_bias"), &L.b_qkv, 3 * m.d) || need(e, K("self_attn.out_proj.bias"), &L.b_out, m.d) ||
+            need(e, K("linear1.bias"), &L.b_ff1, m.F) || need(e, K("linear2.bias"), &L.b_ff2, m.d) ||
+            need(e, K("norm1.weight"), &L.ln1_g, m.d) || need(e, K("norm1.bias"), &L.ln1_b, m.d) ||
+            need(e, K("norm2.weight"), &L.ln2_g, m.d) || need(e, K("norm2.bias"), &L.ln2_b, m.d))
+            return -1;
+        VCB_CUDA_OK(cudaDeviceSynchronize());
+        free_weight_f32(e, K("self_attn.in_proj_weight"));
+        free_weight_f32(e, K("self_attn.out_proj.weight"));
+        free_weight_f32(e, K("linear1.weight"));
+        free_weight_f32(e, K("linear2.weight"));
+        // KV pool for this layer
+        const size_t elems = static_cast<size_t>(e->n_pages) * m.H * KV_PAGE * m.hd;
+        const size_t bytes = elems * (e->kv_fp32 ? 4 : 2);
+        if (!L.kpool) {
+            VCB_CUDA_OK(cudaMalloc(&L.kpool, bytes));
+            VCB_CUDA_OK(cudaMalloc(&L.vpool, bytes));
+            VCB_CUDA_OK(cudaMemset(L.kpool, 0, bytes));
+            VCB_CUDA_OK(cudaMemset(L.vpool, 0, bytes));
+        }
+    }
+    if (need(e, "decoder.norm.weight", &e->lnf_g, m.d) || need(e, "decoder.norm.bias", &e->lnf_b, m.d)) return -1;
+    if (need(e, "text_embedding.word_embeddings.weight", &e->E_text, static_cast<size_t>(m.n_text) * m.d)) return -1;
+    if (need(e, "mask_embedding", &e->mask_emb, static_cast<size_t>(m.max_n_spans) * m.d)) return -1;
+    float *al_t, *al_a;
+    if (need(e, "text_positional_embedding.alpha", &al_t, 1) || need(e, "audio_positional_embedding.alpha", &al_a, 1)) return -1;
+    VCB_CUDA_OK(cudaMemcpy(&e->alpha_t, al_t, 4, cudaMemcpyDeviceToHost));
+    VCB_CUDA_OK(cudaMemcpy(&e->alpha_a, al_a, 4, cudaMemcpyDeviceToHost));
+    // logit heads: stack the K first-stage matrices / biases
+    {
+        const size_t per = static_cast<size_t>(m.Hh) * m.d;
+        float* stacked = nullptr;
+        VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&stacked), per * m.K * sizeof(float)));
+        if (!e->b_h1) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->b_h1), static_cast<size_t>(m.K) * m.Hh * 4));
+        std::vector<float*> b2(m.K), ea(m.K);
+        for (int k = 0; k < m.K; ++k) {
+            float *w0, *b0;
+            snprintf(key, sizeof(key), "predict_layer.%d.0.weight", k);
+            if (need(e, key, &w0, per)) return -1;
+            VCB_CUDA_OK(cudaMemcpy(stacked + per * k, w0, per * 4, cudaMemcpyDeviceToDevice));
+            free_weight_f32(e, key);
+            snprintf(key, sizeof(key), "predict_layer.%d.0.bias", k);
+            if (need(e, key, &b0, m.Hh)) return -1;
+            VCB_CUDA_OK(cudaMemcpy(e->b_h1 + static_cast<size_t>(k) * m.Hh, b0, m.Hh * 4, cudaMemcpyDeviceToDevice));
+            snprintf(key, sizeof(key), "predict_layer.%d.2.weight", k);
+            if (to_bf16_matrix(e, key, &e->h2[k], m.V, m.Hh)) return -1;
+            VCB_CUDA_OK(cudaDeviceSynchronize());
+            free_weight_f32(e, key);
+            snprintf(key, sizeof(key), "predict_layer.%d.2.bias", k);
+            if (need(e, key, &b2[k], m.V)) return -1;
+            snprintf(key, sizeof(key), "audio_embedding.%d.word_embeddings.weight", k);
+            if (need(e, key, &ea[k], static_cast<size_t>(m.V) * m.d)) return -1;
+        }
+        e->f32["__h1_stacked"] = stacked;
+        e->shapes["__h1_stacked"] = {static_cast<int64_t>(m.K) * m.Hh, m.d};
+        if (to_bf16_matrix(e, "__h1_stacked", &e->h1, m.K * m.Hh, m.d)) return -1;
+        VCB_CUDA_OK(cudaDeviceSynchronize());
+        free_weight_f32(e, "__h1_stacked");
+        if (!e->d_bias2) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_bias2), m.K * sizeof(float*)));
+        if (!e->d_E_audio) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_E_audio), m.K * sizeof(float*)));
+        VCB_CUDA_OK(cudaMemcpy(e->d_bias2, b2.data(), m.K * sizeof(float*), cudaMemcpyHostToDevice));
+        VCB_CUDA_OK(cudaMemcpy(e->d_E_audio, ea.data(), m.K * sizeof(float*), cudaMemcpyHostToDevice));
+    }
+    // workspaces
+    if (!e->x_rows) {
+        const int R = vcb_engine::MAX_ROWS, S = e->cfg.max_slots;
+        const int KH = m.K * m.Hh;
+        if (dalloc(&e->x_rows, static_cast<size_t>(R) * m.d) || dalloc(&e->qbuf, static_cast<size_t>(R) * m.d) ||
+            dalloc(&e->x_slot, static_cast<size_t>(S) * m.d) || dalloc(&e->h_slot, static_cast<size_t>(S) * m.d) ||
+            dalloc(&e->act_d, static_cast<size_t>(2 * R) * m.d) || dalloc(&e->act_f, static_cast<size_t>(2 * R) * m.F) ||
+            dalloc(&e->act_h, static_cast<size_t>(2 * R) * KH))
+            return -1;
+        const int widest = std::max(std::max(3 * m.d, m.F), std::max(KH, m.K * m.Vpad));
+        e->partial_floats = static_cast<size_t>(16) * R * widest;
+        if (dalloc(&e->partial, 2 * e->partial_floats)) return -1;
+        if (dalloc(&e->row_slot, R) || dalloc(&e->row_pos, R) || dalloc(&e->row_last, R) ||
+            dalloc(&e->d_slots, R) || dalloc(&e->page_table, static_cast<size_t>(S) * e->max_pages_per_slot) ||
+            dalloc(&e->tok_log, static_cast<size_t>(S) * e->cfg.max_new_tokens * m.K) ||
+            dalloc(&e->dbg_logits, static_cast<size_t>(R) * m.K * m.V) || dalloc(&e->st, S) || dalloc(&e->gr, S) ||
+            dalloc(&e->d_seqs, S))
+            return -1;
+        e->all_rows_cap = static_cast<size_t>(S) * e->cfg.max_seq_len;
+        if (dalloc(&e->all_rows, 4 * e->all_rows_cap)) return -1;
+        e->h_stage_ints = 4096;
+        VCB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_stage), e->h_stage_ints * sizeof(int)));
+        VCB_CUDA_OK(cudaEventCreateWithFlags(&e->stage_ev, cudaEventDisableTiming));
+        const int bp[4] = {16, 32, 64, 128};
+        for (int i = 0; i < 4; ++i) {
+            if (make_tmap_bf16_2d(&e->tm_act_d[i], e->act_d, 2 * bp[i], m.d, m.d, 2 * bp[i]) ||
+                make_tmap_bf16_2d(&e->tm_act_f[i], e->act_f, 2 * bp[i], m.F, m.F, 2 * bp[i]) ||
+                make_tmap_bf16_2d(&e->tm_act_h[i], e->act_h, 2 * bp[i], KH, KH, 2 * bp[i]))
+                return -1;
+        }
+    }
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    e->finalized = true;
+    return 0;
+}
+
+int vcb_prefill(vcb_engine* e, const vcb_prompt* prompts, int32_t n, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!e || !e->finalized) {
+        set_error("engine not finalized");
+        return -1;
+    }
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    const ModelDims& m = e->m;
+    // ---- open slots / groups, allocate KV pages, build the row list ------------------------------------
+    std::vector<EmbedSeq> seqs;
+    std::vector<int> r_seq, r_pos, r_slot, r_last;
+    std::vector<SlotState> sst;
+    std::vector<int> sst_slot;
+    std::vector<GroupState> gst;
+    std::vector<int> gst_id;
+    for (int i = 0; i < n; ++i) {
+        const vcb_prompt& P = prompts[i];
+        const int total = P.x_len + P.y_len;
+        if (P.n_copies < 1 || P.slot < 0 || P.slot + P.n_copies > e->cfg.max_slots || total > e->cfg.max_seq_len ||
+            P.x_len < 1 || P.y_len < 1 || P.n_more_spans > 8) {
+            set_error("prompt %d: bad slot/length (slot=%d copies=%d x_len=%d y_len=%d max_seq_len=%d)", i, P.slot,
+                      P.n_copies, P.x_len, P.y_len, e->cfg.max_seq_len);
+            return -1;
+        }
+        if (e->free_groups.empty()) {
+            set_error("no free group");
+            return -1;
+        }
+        const int gid = e->free_groups.back();
+        e->free_groups.pop_back();
+        GroupState G;
+        memset(&G, 0, sizeof(G));
+        G.mode = P.mode;
+        G.size = P.n_copies;
+        G.keep = P.n_copies == 1 ? 0 : -1;
+        G.spans_left = P.n_more_spans;
+        for (int j = 0; j < 8; ++j) G.more_mask[j] = j < P.n_more_spans ? P.more_mask_rows[j] : 0;
+        G.first_slot = P.slot;
+        gst.push_back(G);
+        gst_id.push_back(gid);
+        EmbedSeq es;
+        es.text_ids = reinterpret_cast<const long long*>(P.text_ids_dev);
+        es.y_tokens = reinterpret_cast<const long long*>(P.y_tokens_dev);
+        es.mask_rows = P.mask_rows_dev;
+        es.x_len = P.x_len;
+        es.y_len = P.y_len;
+        const int seq_idx = static_cast<int>(seqs.size());
+        seqs.push_back(es);
+        for (int c = 0; c < P.n_copies; ++c) {
+            const int slot = P.slot + c;
+            if (e->slot_group[slot] >= 0) {
+                set_error("slot %d already open", slot);
+                return -1;
+            }
+            if (static_cast<int>(e->free_pages.size()) < e->max_pages_per_slot) {
+                set_error("KV pool exhausted");
+                return -1;
+            }
+            e->slot_group[slot] = gid;
+            auto& pg = e->slot_pages[slot];
+            pg.clear();
+            for (int p = 0; p < e->max_pages_per_slot; ++p) {
+                pg.push_back(e->free_pages.back());
+                e->free_pages.pop_back();
+            }
+            SlotState S;
+            memset(&S, 0, sizeof(S));
+            S.x_len = P.x_len;
+            S.seq_len = total;
+            S.y_len = P.y_len;
+            S.group = gid;
+            S.member = c;
+            S.prev_token = -1;
+            S.active = 1;
+            sst.push_back(S);
+            sst_slot.push_back(slot);
+            for (int t = 0; t < total; ++t) {
+                r_seq.push_back(seq_idx);
+                r_pos.push_back(t);
+                r_slot.push_back(slot);
+                r_last.push_back(t == total - 1 ? slot : -1);
+            }
+        }
+    }
+    if (seqs.size() > static_cast<size_t>(e->cfg.max_slots)) {
+        set_error("too many prompts");
+        return -1;
+    }
+    // state + page tables (synchronous copies: prefill is a once-per-utterance call)
+    VCB_CUDA_OK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < sst.size(); ++i) {
+        VCB_CUDA_OK(cudaMemcpy(e->st + sst_slot[i], &sst[i], sizeof(SlotState), cudaMemcpyHostToDevice));
+        VCB_CUDA_OK(cudaMemcpy(e->page_table + static_cast<size_t>(sst_slot[i]) * e->max_pages_per_slot,
+                               e->slot_pages[sst_slot[i]].data(), e->max_pages_per_slot * sizeof(int),
+                               cudaMemcpyHostToDevice));
+    }
+    for (size_t i = 0; i < gst.size(); ++i)
+        VCB_CUDA_OK(cudaMemcpy(e->gr + gst_id[i], &gst[i], sizeof(GroupState), cudaMemcpyHostToDevice));
+    VCB_CUDA_OK(cudaMemcpy(e->d_seqs, seqs.data(), seqs.size() * sizeof(EmbedSeq), cudaMemcpyHostToDevice));
+    // ---- chunked prefill: <= 128 rows per pass through the same kernels as a decode step ----------------
+    const size_t total_rows = r_seq.size();
+    if (total_rows > e->all_rows_cap) {
+        set_error("prefill: %zu rows exceed capacity %zu", total_rows, e->all_rows_cap);
+        return -1;
+    }
+    int* t_seq = e->all_rows;
+    int* t_pos = t_seq + e->all_rows_cap;
+    int* t_slot = t_pos + e->all_rows_cap;
+    int* t_last = t_slot + e->all_rows_cap;
+    VCB_CUDA_OK(cudaMemcpy(t_seq, r_seq.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
+    VCB_CUDA_OK(cudaMemcpy(t_pos, r_pos.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
+    VCB_CUDA_OK(cudaMemcpy(t_slot, r_slot.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
+    VCB_CUDA_OK(cudaMemcpy(t_last, r_last.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
+    for (size_t off = 0; off < total_rows; off += vcb_engine::MAX_ROWS) {
+        const int rows = static_cast<int>(std::min<size_t>(vcb_engine::MAX_ROWS, total_rows - off));
+        e->cur_slot = t_slot + off;
+        e->cur_pos = t_pos + off;
+        e->cur_last = t_last + off;
+        embed_rows_kernel<<<rows, 256, 0, st>>>(e->d_seqs, t_seq + off, t_pos + off, e->x_rows, m.d, m.K, e->E_text,
+                                                e->d_E_audio, e->mask_emb, e->pe, e->alpha_t, e->alpha_a);
+        VCB_CUDA_OK(cudaGetLastError());
+        LAUNCH_COUNT(e);
+        if (forward_rows(e, rows, st)) return -1;
+    }
+    return 0;
+}
+
+int vcb_sample(vcb_engine* e, const int32_t* slots, int32_t n, const float* exp_noise_dev, const vcb_sampling* sp,
+               void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!e || !e->finalized || !slots || !sp || !exp_noise_dev) {
+        set_error("vcb_sample: bad argument");
+        return -1;
+    }
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    if (upload_slots(e, slots, n, st)) return -1;
+    return sample_rows(e, n, exp_noise_dev, sp, st);
+}
+
+int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float* exp_noise_dev, const vcb_sampling* sp,
+                    void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!e || !e->finalized || !slots || !sp || !exp_noise_dev) {
+        set_error("vcb_decode_step: bad argument");
+        return -1;
+    }
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    if (upload_slots(e, slots, n, st)) return -1;
+    step_prep_kernel<<<n, 256, 0, st>>>(e->d_slots, n, e->st, e->gr, e->row_slot, e->row_pos, e->row_last, e->x_slot,
+                                        e->x_rows, e->m.d);
+    VCB_CUDA_OK(cudaGetLastError());
+    LAUNCH_COUNT(e);
+    e->cur_slot = e->row_slot;
+    e->cur_pos = e->row_pos;
+    e->cur_last = e->row_last;
+    if (forward_rows(e, n, st)) return -1;
+    return sample_rows(e, n, exp_noise_dev, sp, st);
+}
+
+int vcb_poll(vcb_engine* e, const int32_t* slots, int32_t n, vcb_status* out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    VCB_CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) {
+        const int slot = slots[i];
+        if (slot < 0 || slot >= e->cfg.max_slots || e->slot_group[slot] < 0) {
+            set_error("slot %d is not open", slot);
+            return -1;
+        }
+        SlotState S;
+        GroupState G;
+        VCB_CUDA_OK(cudaMemcpy(&S, e->st + slot, sizeof(S), cudaMemcpyDeviceToHost));
+        VCB_CUDA_OK(cudaMemcpy(&G, e->gr + e->slot_group[slot], sizeof(G), cudaMemcpyDeviceToHost));
+        out[i].done = G.done;
+        out[i].forced = S.forced;
+        out[i].n_steps = S.n_steps;
+        out[i].keep = G.keep;
+        out[i].n_spans_done = G.n_spans_done;
+        for (int j = 0; j < 8; ++j) out[i].span_ends[j] = G.span_ends[j];
+    }
+    return 0;
+}
+
+int vcb_read_tokens(vcb_engine* e, int32_t slot, int32_t* out_host, int32_t max_steps, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    VCB_CUDA_OK(cudaStreamSynchronize(st));
+    const int nn = std::min(max_steps, e->cfg.max_new_tokens);
+    VCB_CUDA_OK(cudaMemcpy(out_host, e->tok_log + static_cast<size_t>(slot) * e->cfg.max_new_tokens * e->m.K,
+                           static_cast<size_t>(nn) * e->m.K * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int vcb_release(vcb_engine* e, int32_t slot, int32_t n_copies) {
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    int gid = -1;
+    for (int c = 0; c < n_copies; ++c) {
+        const int s = slot + c;
+        if (s < 0 || s >= e->cfg.max_slots || e->slot_group[s] < 0) continue;
+        gid = e->slot_group[s];
+        e->slot_group[s] = -1;
+        for (int p : e->slot_pages[s]) e->free_pages.push_back(p);
+        e->slot_pages[s].clear();
+        VCB_CUDA_OK(cudaMemset(e->st + s, 0, sizeof(SlotState)));
+    }
+    if (gid >= 0) e->free_groups.push_back(gid);
+    return 0;
+}
+
+int vcb_debug_logits(vcb_engine* e, float* out_dev, int32_t n_rows) {
+    VCB_CUDA_OK(cudaMemcpy(out_dev, e->dbg_logits, static_cast<size_t>(n_rows) * e->m.V * sizeof(float),
+                           cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+// Bring-up hook: out[b][n] = sum_k W[n][k] * X[b][k] through the production GEMM (bf16 weights, hi/lo activations).
+int vcb_debug_gemm(const float* W_dev, const float* X_dev, float* out_dev, int32_t N, int32_t Kd, int32_t B,
+                   int32_t splits, int32_t simt) {
+    const int bpad = bpad_for(B);
+    if (B > 128 || Kd % 64) {
+        set_error("vcb_debug_gemm: B <= 128 and K %% 64 == 0 required");
+        return -1;
+    }
+    __nv_bfloat16 *w = nullptr, *x = nullptr;
+    float *xs = nullptr, *partial = nullptr;
+    const int ldp = (N + 3) & ~3;
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, 0);
+    if (splits <= 0) splits = gemm_pick_splits(N, Kd, num_sms);
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&w), static_cast<size_t>(N) * Kd * 2));
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&x), static_cast<size_t>(2 * bpad) * Kd * 2));
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&xs), static_cast<size_t>(bpad) * Kd * 4));
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&partial), static_cast<size_t>(splits) * bpad * ldp * 4));
+    VCB_CUDA_OK(cudaMemset(xs, 0, static_cast<size_t>(bpad) * Kd * 4));
+    VCB_CUDA_OK(cudaMemset(x, 0, static_cast<size_t>(2 * bpad) * Kd * 2));
+    VCB_CUDA_OK(cudaMemcpy(xs, X_dev, static_cast<size_t>(B) * Kd * 4, cudaMemcpyDeviceToDevice));
+    f32_to_bf16_kernel<<<512, 256>>>(W_dev, w, static_cast<size_t>(N) * Kd);
+    // identity "activation" = hi/lo split of X (no bias: pass a zero partial-less path through bias_act with nsplit = 1)
+    VCB_CUDA_OK(cudaMemset(partial, 0, static_cast<size_t>(splits) * bpad * ldp * 4));
+    {
+        // reuse bias_act_kernel: partial := X (ldp = Kd), bias := zeros
+        float* zero = nullptr;
+        VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&zero), static_cast<size_t>(Kd) * 4));
+        VCB_CUDA_OK(cudaMemset(zero, 0, static_cast<size_t>(Kd) * 4));
+        bias_act_kernel<<<dim3((Kd + 255) / 256, B), 256>>>(xs, 1, Kd, bpad, zero, Kd, 0, x, Kd);
+        VCB_CUDA_OK(cudaDeviceSynchronize());
+        cudaFree(zero);
+    }
+    CUtensorMap tmA, tmB;
+    if (make_tmap_bf16_2d(&tmA, w, N, Kd, Kd, 128) || make_tmap_bf16_2d(&tmB, x, 2 * bpad, Kd, Kd, 2 * bpad)) return -1;
+    GemmCall g;
+    g.tmA = &tmA; g.tmB = &tmB; g.W = w; g.X = x; g.partial = partial;
+    g.Nout = N; g.Kdim = Kd; g.ldx = Kd; g.ldp = ldp; g.bpad = bpad; g.splits = splits; g.nvalid = B; g.simt = simt;
+    if (gemm_launch(g, 0)) return -1;
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    // reduce partials on the host side of the ABI with a tiny kernel: reuse reduce_rows_kernel (x_in = zeros)
+    {
+        float* zx = nullptr; float* zb = nullptr; int* idx = nullptr;
+        VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&zx), static_cast<size_t>(bpad) * N * 4));
+        VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&zb), static_cast<size_t>(N) * 4));
+        VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&idx), bpad * sizeof(int)));
+        VCB_CUDA_OK(cudaMemset(zx, 0, static_cast<size_t>(bpad) * N * 4));
+        VCB_CUDA_OK(cudaMemset(zb, 0, static_cast<size_t>(N) * 4));
+        std::vector<int> h(bpad);
+        for (int i = 0; i < bpad; ++i) h[i] = i < B ? i : -1;
+        VCB_CUDA_OK(cudaMemcpy(idx, h.data(), bpad * sizeof(int), cudaMemcpyHostToDevice));
+        reduce_rows_kernel<<<B, 256>>>(zx, partial, splits, ldp, bpad, zb, out_dev, idx, N);
+        VCB_CUDA_OK(cudaDeviceSynchronize());
+        cudaFree(zx); cudaFree(zb); cudaFree(idx);
+    }
+    cudaFree(w); cudaFree(x); cudaFree(xs); cudaFree(partial);
+    return 0;
+}
+
+int vcb_set_option(vcb_engine* e, const char* name, int32_t value) {
+    if (!strcmp(name, "gemm_simt")) e->opt_simt = value;
+    else if (!strcmp(name, "pdl")) e->opt_pdl = value;
+    else {
+        set_error("unknown option %s", name);
+        return -1;
+    }
+    return 0;
+}
+
+int64_t vcb_counter(vcb_engine* e, const char* name) {
+    if (!strcmp(name, "launches")) return e->n_launches;
+    if (!strcmp(name, "num_sms")) return e->num_sms;
+    if (!strcmp(name, "kv_bytes_per_token")) return static_cast<int64_t>(e->m.L) * 2 * e->m.d * (e->kv_fp32 ? 4 : 2);
+    return -1;
+}
+
+int vcb_delay_pattern(const int64_t* z_dev, int64_t* out_dev, int32_t B, int32_t K, int32_t T, int64_t special_token,
+                      void* stream) {
+    if (B <= 0 || K <= 0 || T < 0) {
+        set_error("vcb_delay_pattern: bad shape");
+        return -1;
+    }
+    const int S = T + K;
+    dim3 grid((S + 255) / 256, B * K);
+    delay_pattern_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(z_dev), reinterpret_cast<long long*>(out_dev), K, T, special_token);
+    VCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

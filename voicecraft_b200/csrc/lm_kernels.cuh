@@ -1,0 +1,801 @@
+// Device kernels of the codec-LM decode path (everything except the tcgen05 GEMM).
+// All of them are HBM/L2-bound integer or fp32 work: coalesced 16-byte accesses, warp-level reductions,
+// TMA bulk copies for the paged KV cache.  Included only by lm_engine.cu.
+#pragma once
+#include "vcb_internal.h"
+
+namespace vcb {
+
+static constexpr int KV_PAGE = 64;          // tokens per KV page
+static constexpr int ATT_THREADS = 128;
+static constexpr int ATT_STAGES = 2;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Prompt embedding:  text rows  x = E_text[id] + alpha_t * PE[i]          (voicecraft.py:950-951)
+//                    audio rows x = sum_k E_k[tok_k] (or mask_embedding[r]) + alpha_a * PE[j]   (:978-985, 311-320)
+// One CTA per row of the prefill chunk.  fp32 throughout; alpha*pe is rounded before the add, like eager torch.
+// ---------------------------------------------------------------------------------------------------
+struct EmbedSeq {
+    const long long* text_ids;
+    const long long* y_tokens;   // [y_len][K]
+    const int* mask_rows;        // [y_len] or null
+    int x_len, y_len;
+};
+
+__global__ void embed_rows_kernel(const EmbedSeq* __restrict__ seqs, const int* __restrict__ row_seq,
+                                  const int* __restrict__ row_pos, float* __restrict__ x_rows, int d, int K,
+                                  const float* __restrict__ E_text, const float* const* __restrict__ E_audio,
+                                  const float* __restrict__ mask_emb, const float* __restrict__ pe, float alpha_t,
+                                  float alpha_a) {
+    const int r = blockIdx.x;
+    const EmbedSeq s = seqs[row_seq[r]];
+    const int pos = row_pos[r];
+    float* out = x_rows + static_cast<size_t>(r) * d;
+    if (pos < s.x_len) {
+        const float* e = E_text + static_cast<size_t>(s.text_ids[pos]) * d;
+        const float* p = pe + static_cast<size_t>(pos) * d;
+        for (int c = threadIdx.x; c < d; c += blockDim.x) out[c] = __fadd_rn(e[c], __fmul_rn(alpha_t, p[c]));
+    } else {
+        const int j = pos - s.x_len;
+        const float* p = pe + static_cast<size_t>(j) * d;
+        const int mr = s.mask_rows ? s.mask_rows[j] : -1;
+        for (int c = threadIdx.x; c < d; c += blockDim.x) {
+            float acc;
+            if (mr >= 0) {
+                acc = mask_emb[static_cast<size_t>(mr) * d + c];
+            } else {
+                acc = 0.f;
+                for (int k = 0; k < K; ++k) {
+                    const float v = E_audio[k][static_cast<size_t>(s.y_tokens[static_cast<size_t>(j) * K + k]) * d + c];
+                    acc = (k == 0) ? v : __fadd_rn(acc, v);
+                }
+            }
+            out[c] = __fadd_rn(acc, __fmul_rn(alpha_a, p[c]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row reduce + LayerNorm:  x' = x[src] + bias + sum_z partial[z][row]   (residual + split-K reduce, fixed z order)
+//                          y  = LN(x') * gamma + beta  ->  bf16 hi / lo rows of the next GEMM's B operand
+// Replaces F.layer_norm (transformer.py:62-75) and the residual adds (:321-329).
+// ---------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ x_in, const int* __restrict__ src_index, float* __restrict__ x_out,
+               const float* __restrict__ partial, int nsplit, int ldp, int bpad, const float* __restrict__ bias,
+               const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ act,
+               int ld_act, int d, float eps) {
+    __shared__ float red[8];
+    pdl_wait();
+    const int r = blockIdx.x;
+    const int src = src_index ? src_index[r] : r;
+    float v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int c = threadIdx.x + j * 256;
+        float t = 0.f;
+        if (c < d) {
+            t = x_in[static_cast<size_t>(src) * d + c];
+            if (nsplit > 0) {
+                float u = bias[c];
+                for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
+                t += u;
+            }
+            if (x_out) x_out[static_cast<size_t>(r) * d + c] = t;
+        }
+        v[j] = t;
+        s += t;
+    }
+    const float mean = block_sum_256(s, red) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int c = threadIdx.x + j * 256;
+        if (c < d) {
+            const float dv = v[j] - mean;
+            q += dv * dv;
+        }
+    }
+    const float var = block_sum_256(q, red) / d;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    pdl_launch_dependents();
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int c = threadIdx.x + j * 256;
+        if (c < d) {
+            const float y = (v[j] - mean) * rstd * gamma[c] + beta[c];
+            __nv_bfloat16 hi, lo;
+            split_bf16(y, hi, lo);
+            act[static_cast<size_t>(r) * ld_act + c] = hi;
+            act[static_cast<size_t>(r + bpad) * ld_act + c] = lo;
+        }
+    }
+}
+
+// x' = x + bias + sum_z partial  ->  out[out_index[row]]   (hidden state of the last token of each utterance)
+__global__ void reduce_rows_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int nsplit,
+                                   int ldp, int bpad, const float* __restrict__ bias, float* __restrict__ out,
+                                   const int* __restrict__ out_index, int d) {
+    pdl_wait();
+    const int r = blockIdx.x;
+    const int dst = out_index[r];
+    if (dst < 0) return;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float u = bias[c];
+        for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
+        out[static_cast<size_t>(dst) * d + c] = x_in[static_cast<size_t>(r) * d + c] + u;
+    }
+}
+
+// act = f(sum_z partial + bias) -> bf16 hi/lo.  f: 1 = ReLU (transformer.py:387), 2 = exact GELU (voicecraft.py:183)
+__global__ void bias_act_kernel(const float* __restrict__ partial, int nsplit, int ldp, int bpad,
+                                const float* __restrict__ bias, int N, int act_kind,
+                                __nv_bfloat16* __restrict__ act, int ld_act) {
+    pdl_wait();
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float u = bias[c];
+    for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
+    if (act_kind == 1) u = fmaxf(u, 0.f);
+    else if (act_kind == 2) u = 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f));
+    __nv_bfloat16 hi, lo;
+    split_bf16(u, hi, lo);
+    act[static_cast<size_t>(r) * ld_act + c] = hi;
+    act[static_cast<size_t>(r + bpad) * ld_act + c] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// QKV finish: q -> fp32 [rows, d]; k, v -> appended in place to the paged KV cache at (slot, pos).
+// Replaces the unflatten/transpose copy (activation.py:88) and BOTH cache re-allocations
+// (activation.py:627-631 torch.cat per layer, voicecraft.py:1081 torch.cat of the whole cache).
+// KV pool layout per layer: [page][head][KV_PAGE tokens][hd]  -> one (page, head) slab is contiguous.
+// ---------------------------------------------------------------------------------------------------
+template <typename KVT>
+__global__ void qkv_finish_kernel(const float* __restrict__ partial, int nsplit, int ldp, int bpad,
+                                  const float* __restrict__ bias, float* __restrict__ qbuf, KVT* __restrict__ kpool,
+                                  KVT* __restrict__ vpool, const int* __restrict__ page_table, int max_pages,
+                                  const int* __restrict__ row_slot, const int* __restrict__ row_pos, int d, int H,
+                                  int hd) {
+    pdl_wait();
+    const int r = blockIdx.x;
+    const int pos = row_pos[r];
+    if (pos < 0) return;
+    const int slot = row_slot[r];
+    const int page = page_table[slot * max_pages + pos / KV_PAGE];
+    const int tok = pos % KV_PAGE;
+    for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
+        float u = bias[c];
+        for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
+        const int part = c / d, cc = c - part * d;
+        if (part == 0) {
+            qbuf[static_cast<size_t>(r) * d + cc] = u;
+        } else {
+            const int h = cc / hd, e = cc - h * hd;
+            const size_t off = ((static_cast<size_t>(page) * H + h) * KV_PAGE + tok) * hd + e;
+            KVT* pool = (part == 1) ? kpool : vpool;
+            if constexpr (sizeof(KVT) == 2) pool[off] = __float2bfloat16_rn(u);
+            else pool[off] = u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Attention over the paged KV cache, one CTA per (row, head).  q-length 1 per row (decode step, or one
+// token of a prefill chunk): keys 0..pos of the row's own utterance -- the causal mask over [text;audio]
+// of voicecraft.py:419-447 without ever materialising it.  K/V pages are staged with TMA bulk copies
+// (cp.async.bulk -> UBLKCP) into a 2-stage shared-memory ring guarded by mbarriers; math is fp32 on CUDA
+// cores (1 FLOP/byte: HBM-bound).  Replaces F.scaled_dot_product_attention at activation.py:634.
+//   QK : LPT = hd/8 lanes per key, each lane one 16-byte chunk of the key row (conflict-free), xor-shuffle reduce
+//   PV : warp w owns keys [16w,16w+16) of the page, lane owns hd/32 output dims
+// Output: bf16 hi/lo rows for the out-projection GEMM.
+// ---------------------------------------------------------------------------------------------------
+template <typename KVT, int HD>
+struct AttSmem {
+    static constexpr int PAGE_BYTES = KV_PAGE * HD * sizeof(KVT);
+    static constexpr int OFF_V = ATT_STAGES * PAGE_BYTES;
+    static constexpr int OFF_SC = 2 * ATT_STAGES * PAGE_BYTES;
+    static constexpr int OFF_PW = OFF_SC + KV_PAGE * 4;
+    static constexpr int OFF_RED = OFF_PW + 4 * KV_PAGE * 4;
+    static constexpr int OFF_BAR = OFF_RED + 4 * HD * 4;
+    static constexpr int TOTAL = OFF_BAR + ATT_STAGES * 8 + 128;
+};
+
+template <typename KVT, int N>
+__device__ __forceinline__ void load_kv_vec(const KVT* p, float (&out)[N]) {
+    if constexpr (sizeof(KVT) == 2) {
+        if constexpr (N == 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                out[2 * i] = __uint_as_float(w[i] << 16);
+                out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+        } else if constexpr (N == 4) {
+            const uint2 u = *reinterpret_cast<const uint2*>(p);
+            out[0] = __uint_as_float(u.x << 16);
+            out[1] = __uint_as_float(u.x & 0xffff0000u);
+            out[2] = __uint_as_float(u.y << 16);
+            out[3] = __uint_as_float(u.y & 0xffff0000u);
+        } else {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+            out[0] = __uint_as_float(u << 16);
+            out[1] = __uint_as_float(u & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            const float2 f = *reinterpret_cast<const float2*>(p + i);
+            out[i] = f.x;
+            out[i + 1] = f.y;
+        }
+    }
+}
+
+template <typename KVT, int HD>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, const KVT* __restrict__ vpool,
+                 const int* __restrict__ page_table, int max_pages, const int* __restrict__ row_slot,
+                 const int* __restrict__ row_pos, int H, __nv_bfloat16* __restrict__ act, int ld_act, int bpad,
+                 float scale) {
+    using L = AttSmem<KVT, HD>;
+    constexpr int LPT = HD / 8;          // lanes per key in QK
+    constexpr int TPW = 32 / LPT;        // keys per warp iteration
+    constexpr int DPT = HD / 32;         // output dims per lane in PV
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    KVT* sK = reinterpret_cast<KVT*>(att_smem);
+    KVT* sV = reinterpret_cast<KVT*>(att_smem + L::OFF_V);
+    float* sc = reinterpret_cast<float*>(att_smem + L::OFF_SC);
+    float* pw = reinterpret_cast<float*>(att_smem + L::OFF_PW);
+    float* red = reinterpret_cast<float*>(att_smem + L::OFF_RED);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(att_smem + L::OFF_BAR);
+
+    const int r = blockIdx.x / H, h = blockIdx.x % H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ATT_STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    pdl_wait();
+    const int pos = row_pos[r];
+    if (pos < 0) return;
+    const int slot = row_slot[r];
+    const int npages = pos / KV_PAGE + 1;
+    const int* pt = page_table + slot * max_pages;
+    __syncthreads();
+
+    auto issue = [&](int p) {
+        const int s = p % ATT_STAGES;
+        const size_t off = (static_cast<size_t>(pt[p]) * H + h) * KV_PAGE * HD;
+        mbar_arrive_expect_tx(&bar[s], 2 * L::PAGE_BYTES);
+        tma_bulk_g2s(sK + s * KV_PAGE * HD, kpool + off, L::PAGE_BYTES, &bar[s]);
+        tma_bulk_g2s(sV + s * KV_PAGE * HD, vpool + off, L::PAGE_BYTES, &bar[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int p = 0; p < min(npages, ATT_STAGES); ++p) issue(p);
+
+    const int sub = lane % LPT;
+    float q[8];
+    {
+        const float* qp = qbuf + (static_cast<size_t>(r) * H + h) * HD + sub * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = qp[i];
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[DPT];
+#pragma unroll
+    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+
+    for (int p = 0; p < npages; ++p) {
+        const int s = p % ATT_STAGES;
+        mbar_wait(&bar[s], (p / ATT_STAGES) & 1);
+        const KVT* K = sK + s * KV_PAGE * HD;
+        const KVT* V = sV + s * KV_PAGE * HD;
+        // ---- scores for this warp's 16 keys
+#pragma unroll
+        for (int it = 0; it < 16 / TPW; ++it) {
+            const int t = warp * 16 + it * TPW + lane / LPT;
+            float kv[8];
+            load_kv_vec<KVT, 8>(K + t * HD + sub * 8, kv);
+            float dsum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dsum = fmaf(q[i], kv[i], dsum);
+#pragma unroll
+            for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+            if (sub == 0) sc[t] = (p * KV_PAGE + t <= pos) ? dsum * scale : -INFINITY;
+        }
+        __syncthreads();
+        // ---- online softmax bookkeeping (every warp redundantly over all 64 scores: identical m, l)
+        const float s0 = sc[lane], s1 = sc[lane + 32];
+        const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
+        const float corr = expf(m_run - m_new);
+        const float p0 = expf(s0 - m_new), p1 = expf(s1 - m_new);
+        float* mypw = pw + warp * KV_PAGE;
+        mypw[lane] = p0;
+        mypw[lane + 32] = p1;
+        l_run = l_run * corr + warp_sum(p0 + p1);
+        m_run = m_new;
+        __syncwarp();
+        // ---- PV for this warp's 16 keys
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) acc[i] *= corr;
+#pragma unroll 4
+        for (int tt = 0; tt < 16; ++tt) {
+            const int t = warp * 16 + tt;
+            const float pt_ = mypw[t];
+            float vv[DPT];
+            load_kv_vec<KVT, DPT>(V + t * HD + lane * DPT, vv);
+#pragma unroll
+            for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
+        }
+        __syncthreads();                                   // everyone is done with stage s
+        if (threadIdx.x == 0 && p + ATT_STAGES < npages) issue(p + ATT_STAGES);
+    }
+    pdl_launch_dependents();
+    // ---- combine the 4 warps' partial outputs
+#pragma unroll
+    for (int i = 0; i < DPT; ++i) red[warp * HD + lane * DPT + i] = acc[i];
+    __syncthreads();
+    for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
+        const float o = (red[dd] + red[HD + dd] + red[2 * HD + dd] + red[3 * HD + dd]) / l_run;
+        __nv_bfloat16 hi, lo;
+        split_bf16(o, hi, lo);
+        const size_t c = static_cast<size_t>(h) * HD + dd;
+        act[static_cast<size_t>(r) * ld_act + c] = hi;
+        act[static_cast<size_t>(r + bpad) * ld_act + c] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Step prologue: assign each row its position, advance the per-slot counters, fetch the input embedding
+// produced by the previous sampler call.
+// ---------------------------------------------------------------------------------------------------
+__global__ void step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ st,
+                                 const GroupState* __restrict__ gr, int* __restrict__ row_slot,
+                                 int* __restrict__ row_pos, int* __restrict__ row_last,
+                                 const float* __restrict__ x_slot, float* __restrict__ x_rows, int d) {
+    const int r = blockIdx.x;
+    const int slot = slots[r];
+    __shared__ int s_pos;
+    if (threadIdx.x == 0) {
+        SlotState& S = st[slot];
+        const bool on = S.active && !gr[S.group].done;
+        s_pos = on ? S.seq_len : -1;
+        row_slot[r] = slot;
+        row_pos[r] = s_pos;
+        row_last[r] = on ? slot : -1;
+        if (on) {
+            S.seq_len += 1;
+            S.y_len += 1;
+        }
+    }
+    __syncthreads();
+    if (s_pos < 0) return;
+    for (int c = threadIdx.x; c < d; c += blockDim.x)
+        x_rows[static_cast<size_t>(r) * d + c] = x_slot[static_cast<size_t>(slot) * d + c];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused sampler: one CTA per (utterance, codebook) row of V logits.  Reproduces, without a host sync,
+//   * the in-place logit edits of sample_helper (voicecraft.py:1018-1067 tts, :718-787 edit, :1269-1325 batch)
+//   * temperature, top-k (strict '<' vs the k-th largest value), top-p (sorted cumulative softmax, shift by one),
+//     softmax and torch.multinomial(.,1) == argmax(p / q) with caller-provided q ~ Exp(1)   (:26-86)
+//   * empty-token forcing, end-token trigger (sample / argmax / length cap), silence bookkeeping, the K-1 step
+//     end cascade, best-of-N `keep`, multi-span hand-over; and it emits the next input embedding
+//     sum_k E_k[tok_k] + alpha * PE[t]                                                   (:1102-1116)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2key(float x) {        // order-preserving float -> uint
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct SamplerArgs {
+    const int* slots;
+    int n;
+    SlotState* st;
+    GroupState* gr;
+    const float* partial;     // logits partials [nsplit][bpad][ldp], column = k*Vpad + v
+    int nsplit, ldp, bpad;
+    const float* const* bias2;   // [K] -> [V]
+    const float* noise;       // [n*K][V]
+    float* dbg_logits;        // [n*K][V] or null
+    int* tok_log;             // [max_slots][max_steps][K]
+    int max_steps;
+    float* x_slot;            // [max_slots][d]
+    const float* const* E_audio;
+    const float* mask_emb;
+    const float* pe;
+    float alpha_a;
+    int d, K, V, Vpad;
+    int empty_token, eog, eos, encodec_sr;
+    SamplingParams sp;
+};
+
+static constexpr int SAMP_THREADS = 256;
+static constexpr int SAMP_MAXV = 12;       // V <= 3072
+static constexpr int SAMP_SORT_N = 4096;
+
+__device__ void sampler_finish_slot(const SamplerArgs& a, int slot, float* sred);
+
+__global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs a) {
+    __shared__ float sred[8];
+    __shared__ int sidx[8];
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_kleft;
+    __shared__ int s_flag;
+    extern __shared__ unsigned long long sort_buf[];     // SAMP_SORT_N entries (only used when top_p < 1)
+
+    pdl_wait();
+    const int i = blockIdx.x / a.K, k = blockIdx.x % a.K;
+    const int slot = a.slots[i];
+    SlotState& S = a.st[slot];
+    if (!S.active) return;
+    GroupState& G = a.gr[S.group];
+    if (G.done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K, V = a.V;
+
+    if (S.forced > 0) {
+        // edit-mode hand-over to the next span (voicecraft.py:838-858): this forward fed a forced embedding,
+        // nothing is sampled; prepare the next forced input.
+        if (k != 0) return;
+        const int f = S.forced;                 // 2: next input = mask embedding, 1: next input = empty-token embedding
+        const float* pe = a.pe + static_cast<size_t>(S.y_len) * a.d;
+        for (int c = tid; c < a.d; c += SAMP_THREADS) {
+            float acc;
+            if (f == 2) {
+                acc = a.mask_emb[static_cast<size_t>(G.more_mask[0]) * a.d + c];
+            } else {
+                acc = 0.f;
+                for (int kk = 0; kk < K; ++kk) {
+                    const float v = a.E_audio[kk][static_cast<size_t>(a.empty_token) * a.d + c];
+                    acc = kk == 0 ? v : __fadd_rn(acc, v);
+                }
+            }
+            a.x_slot[static_cast<size_t>(slot) * a.d + c] = __fadd_rn(acc, __fmul_rn(a.alpha_a, pe[c]));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (f == 2) {                       // consume the mask row
+                for (int j = 0; j < 7; ++j) G.more_mask[j] = G.more_mask[j + 1];
+            }
+            S.forced = f - 1;
+        }
+        return;
+    }
+
+    const bool tts = G.mode == 0;
+    const int E = tts ? (a.eos > 0 ? a.eos : a.eog) : a.eog;
+    const int n_eog = G.n_eog, cur = G.cur_num_gen;
+    const int row = i * K + k;
+
+    // ---- load logits (split-K reduce + bias), apply the reference's in-place edits -----------------
+    float l[SAMP_MAXV];
+#pragma unroll
+    for (int j = 0; j < SAMP_MAXV; ++j) {
+        const int v = tid + j * SAMP_THREADS;
+        float u = -INFINITY;
+        if (v < V) {
+            u = a.bias2[k][v];
+            for (int z = 0; z < a.nsplit; ++z)
+                u += a.partial[(static_cast<size_t>(z) * a.bpad + i) * a.ldp + k * a.Vpad + v];
+            if (a.dbg_logits) a.dbg_logits[static_cast<size_t>(row) * V + v] = u;
+            if (a.eos > 0 && v == (tts ? a.eog : a.eos)) u = -10000.f;                   // :1091-1093 / :816-818
+            if (n_eog == 0) {
+                if (k >= 1 && (v == E || v == a.empty_token)) u = -10000.f;                // :1021-1023
+                if (k == 0 && tts && cur <= a.encodec_sr / 5 && v == E) u = -10000.f;     // :1024-1025
+                if (k == 0 && a.sp.stop_repetition > 0 && v == S.prev_token && S.consec > a.sp.stop_repetition) {
+                    bool sil = false;
+                    for (int t = 0; t < a.sp.n_silence; ++t) sil |= (a.sp.silence_tokens[t] == v);
+                    if (sil) {                                                             // :1027-1031
+                        const float f = static_cast<float>(S.consec - (a.sp.stop_repetition - 1));
+                        u = (u < 0.f) ? u * f : u / f;
+                    }
+                }
+            } else {
+                if (k > n_eog && (v == E || v == a.empty_token)) u = -10000.f;            // :1056-1058
+            }
+        }
+        l[j] = u;
+    }
+
+    // ---- argmax of the edited logits (first index wins), needed for the end-token trigger ----------
+    float bm = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < SAMP_MAXV; ++j) {
+        const int v = tid + j * SAMP_THREADS;
+        if (v < V && (l[j] > bm || (l[j] == bm && v < bi))) { bm = l[j]; bi = v; }
+    }
+    auto block_argmax = [&](float& val, int& idx) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { sred[warp] = val; sidx[warp] = idx; }
+        __syncthreads();
+        val = sred[0]; idx = sidx[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+            if (sred[w] > val || (sred[w] == val && sidx[w] < idx)) { val = sred[w]; idx = sidx[w]; }
+    };
+    block_argmax(bm, bi);
+    const int argmax_raw = bi;
+
+    // ---- temperature (:80-81) -----------------------------------------------------------------------
+    if (a.sp.temperature != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < SAMP_MAXV; ++j) l[j] = __fdiv_rn(l[j], a.sp.temperature);
+        bm = __fdiv_rn(bm, a.sp.temperature);
+    }
+
+    // ---- top-k: exact k-th largest by 4-pass radix select on order-preserving keys (:38-44) ----------
+    if (a.sp.top_k > 0) {
+        const int kk = min(max(a.sp.top_k, 1), V);
+        if (tid == 0) { s_prefix = 0; s_kleft = kk; }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+            for (int j = 0; j < SAMP_MAXV; ++j) {
+                const int v = tid + j * SAMP_THREADS;
+                if (v < V) {
+                    const uint32_t key = f2key(l[j]);
+                    if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int left = s_kleft, b = 255;
+                for (; b > 0; --b) {
+                    if (hist[b] >= left) break;
+                    left -= hist[b];
+                }
+                s_kleft = left;
+                s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+            }
+            __syncthreads();
+        }
+        const float thr = key2f(s_prefix);
+#pragma unroll
+        for (int j = 0; j < SAMP_MAXV; ++j)
+            if (l[j] < thr) l[j] = -INFINITY;
+        __syncthreads();
+    }
+
+    // ---- top-p (:46-67): sort descending, softmax, cumulative sum, keep ranks < j0 ---------------------
+    if (a.sp.top_p < 1.0f) {
+        for (int s = tid; s < SAMP_SORT_N; s += SAMP_THREADS) sort_buf[s] = 0ull;   // pads sort last (key 0 < any real key)
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SAMP_MAXV; ++j) {
+            const int v = tid + j * SAMP_THREADS;
+            if (v < V)   // descending by value; ties -> lower index first
+                sort_buf[v] = (static_cast<unsigned long long>(f2key(l[j])) << 32) | static_cast<uint32_t>(0xffffffffu - v);
+        }
+        __syncthreads();
+        for (int size = 2; size <= SAMP_SORT_N; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < SAMP_SORT_N / 2; t += SAMP_THREADS) {
+                    const int lo = 2 * t - (t & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool desc = ((lo & size) == 0);
+                    const unsigned long long x = sort_buf[lo], y = sort_buf[hi];
+                    if ((x < y) == desc) { sort_buf[lo] = y; sort_buf[hi] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        // softmax over the sorted row (max = first element) and inclusive scan in rank order
+        const float smax = key2f(static_cast<uint32_t>(sort_buf[0] >> 32));
+        constexpr int PER = SAMP_SORT_N / SAMP_THREADS;      // 16 consecutive ranks per thread
+        float e[PER];
+        float loc = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int rnk = tid * PER + j;
+            const unsigned long long ent = sort_buf[rnk];
+            e[j] = (rnk < V) ? expf(key2f(static_cast<uint32_t>(ent >> 32)) - smax) : 0.f;
+            loc += e[j];
+        }
+        const float total = block_sum_256(loc, sred);
+        // exclusive prefix of `loc` across threads
+        float incl = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();
+        if (lane == 31) sred[warp] = incl;
+        __syncthreads();
+        float base = 0.f;
+        for (int w = 0; w < warp; ++w) base += sred[w];
+        float run = base + incl - loc;
+        int cnt = 0;                                       // ranks j with cum_j <= top_p
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            run += e[j];
+            const int rnk = tid * PER + j;
+            if (rnk < V && !(run / total > a.sp.top_p)) cnt++;
+        }
+        __syncthreads();
+        const int j0 = static_cast<int>(block_sum_256(static_cast<float>(cnt), sred) + 0.5f) + 1;   // kept ranks: [0, j0)
+        // cum is monotone, so "cum_j <= top_p" holds exactly for ranks [0, j0-1): rank of a value = its sorted position
+        __syncthreads();
+        // mark removed: write per-index flag through the sorted order
+        // reuse hist as nothing; flags go into the low bit trick: store rank into a dense array (aliasing sort_buf upper half)
+        int* rank_of = reinterpret_cast<int*>(sort_buf + SAMP_SORT_N);      // V ints after the sort area
+        for (int rnk = tid; rnk < V; rnk += SAMP_THREADS) {
+            const uint32_t idx = 0xffffffffu - static_cast<uint32_t>(sort_buf[rnk] & 0xffffffffull);
+            rank_of[idx] = rnk;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SAMP_MAXV; ++j) {
+            const int v = tid + j * SAMP_THREADS;
+            if (v < V && rank_of[v] >= j0) l[j] = -INFINITY;
+        }
+        __syncthreads();
+    }
+
+    // ---- softmax + multinomial == argmax(p / q)  (:85) ---------------------------------------------------
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SAMP_MAXV; ++j) mx = fmaxf(mx, l[j]);
+    mx = warp_max(mx);
+    __syncthreads();
+    if (lane == 0) sred[warp] = mx;
+    __syncthreads();
+    mx = sred[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sred[w]);
+    float ev[SAMP_MAXV];
+    float esum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SAMP_MAXV; ++j) {
+        const int v = tid + j * SAMP_THREADS;
+        ev[j] = (v < V) ? expf(l[j] - mx) : 0.f;
+        esum += ev[j];
+    }
+    const float tot = block_sum_256(esum, sred);
+    float best = -1.f;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < SAMP_MAXV; ++j) {
+        const int v = tid + j * SAMP_THREADS;
+        if (v < V) {
+            const float p = ev[j] / tot;
+            const float sc = p / a.noise[static_cast<size_t>(row) * V + v];
+            if (sc > best || (sc == best && v < besti)) { best = sc; besti = v; }
+        }
+    }
+    block_argmax(best, besti);
+    int tok = besti;
+
+    // ---- forced values / end-token logic ----------------------------------------------------------------
+    if (tid == 0) {
+        if (n_eog == 0) {
+            if (cur < K - 1 && k > cur) tok = a.empty_token;                                 // :1037-1039
+            if (k == 0) {
+                const int cap = tts ? S.x_len * (a.encodec_sr / 5) : S.x_len * 10;
+                if (tok == E || argmax_raw == E || S.y_len > cap) {                          // :1041-1045
+                    tok = E;
+                    atomicMax(&G.trig_keep, S.member + 1);
+                }
+            }
+        } else if (G.size == 1 || S.member == G.keep) {                                      // :1063-1066 / :1321-1323
+            if (k < n_eog) tok = a.empty_token;
+            else if (k == n_eog) tok = E;
+        }
+        a.tok_log[(static_cast<size_t>(slot) * a.max_steps + S.n_steps) * K + k] = tok;
+        __threadfence();
+        s_flag = (atomicAdd(&S.arrive, 1) == K - 1);
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    sampler_finish_slot(a, slot, sred);
+}
+
+// Last codebook row of a slot: next input embedding + silence bookkeeping; last slot of a group: group state.
+__device__ void sampler_finish_slot(const SamplerArgs& a, int slot, float* sred) {
+    SlotState& S = a.st[slot];
+    GroupState& G = a.gr[S.group];
+    const int tid = threadIdx.x, K = a.K;
+    const volatile int* toks = a.tok_log + (static_cast<size_t>(slot) * a.max_steps + S.n_steps) * K;
+    const float* pe = a.pe + static_cast<size_t>(S.y_len) * a.d;
+    for (int c = tid; c < a.d; c += SAMP_THREADS) {
+        float acc = 0.f;
+        for (int kk = 0; kk < K; ++kk) {
+            const float v = a.E_audio[kk][static_cast<size_t>(toks[kk]) * a.d + c];
+            acc = kk == 0 ? v : __fadd_rn(acc, v);
+        }
+        a.x_slot[static_cast<size_t>(slot) * a.d + c] = __fadd_rn(acc, __fmul_rn(a.alpha_a, pe[c]));
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    if (G.n_eog == 0) {                                                                     // :1047-1051
+        const int t0 = toks[0];
+        bool sil = false;
+        for (int t = 0; t < a.sp.n_silence; ++t) sil |= (a.sp.silence_tokens[t] == t0);
+        S.consec = (sil && t0 == S.prev_token) ? S.consec + 1 : 0;
+        S.prev_token = t0;
+    }
+    S.n_steps += 1;
+    S.arrive = 0;
+    __threadfence();
+    if (atomicAdd(&G.arrive, 1) != G.size - 1) return;
+    __threadfence();
+    // ---- group finalize
+    G.arrive = 0;
+    if (G.n_eog == 0) {
+        if (G.trig_keep > 0) {
+            G.n_eog = 1;
+            G.keep = G.trig_keep - 1;            // the last member that triggered wins (:1302)
+        }
+    } else {
+        G.n_eog += 1;
+    }
+    G.trig_keep = 0;
+    G.cur_num_gen += 1;
+    if (G.n_eog == K) {                                                                      // span finished
+        if (G.n_spans_done < 8) G.span_ends[G.n_spans_done] = S.n_steps;
+        G.n_spans_done += 1;
+        if (G.mode == 1 && G.spans_left > 0) {
+            G.spans_left -= 1;
+            G.n_eog = 0;
+            G.cur_num_gen = 0;
+            for (int mI = 0; mI < G.size; ++mI) {
+                SlotState& M = a.st[G.first_slot + mI];
+                M.forced = 2;
+                M.prev_token = -1;
+                M.consec = 0;
+            }
+        } else {
+            G.done = 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Delayed codebook pattern gather (integer): out[b,k,s] = z[b,k,s-1-k] if 0 <= s-1-k < T else special.
+// codebooks_patterns.py:151-176 with the DelayedPatternProvider layout (:336-352, delays = 0..K-1).
+// ---------------------------------------------------------------------------------------------------
+__global__ void delay_pattern_kernel(const long long* __restrict__ z, long long* __restrict__ out, int K, int T,
+                                     long long special) {
+    const int S = T + K;
+    const size_t bk = blockIdx.y;
+    const int k = static_cast<int>(bk % K);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const int t = s - 1 - k;
+        out[bk * S + s] = (t >= 0 && t < T) ? z[bk * T + t] : special;
+    }
+}
+
+}  // namespace vcb

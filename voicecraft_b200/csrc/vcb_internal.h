@@ -1,0 +1,81 @@
+// Internal declarations shared by the .cu files of libvcb200.so (not part of the C ABI).
+#pragma once
+#include "vcb_common.cuh"
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace vcb {
+
+// ---------------------------------------------------------------------------------------------------
+// GEMM (gemm_tcgen05.cu)
+// ---------------------------------------------------------------------------------------------------
+struct GemmCall {
+    const CUtensorMap* tmA = nullptr;   // weights [Nout, Kdim]
+    const CUtensorMap* tmB = nullptr;   // activations [2*bpad, ldx]
+    const __nv_bfloat16* W = nullptr;   // raw pointers (simt cross-check path only)
+    const __nv_bfloat16* X = nullptr;
+    float* partial = nullptr;           // [splits][bpad][ldp]
+    int Nout = 0, Kdim = 0, ldx = 0, ldp = 0, bpad = 0, splits = 1, b_col_off = 0, nvalid = 0;
+    int pdl = 0, simt = 0;
+};
+int gemm_launch(const GemmCall& g, cudaStream_t st);
+int gemm_pick_splits(int Nout, int Kdim, int num_sms);
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows);
+
+// ---------------------------------------------------------------------------------------------------
+// Per-utterance ("slot") and per-group device state.  A group couples the slots of one
+// inference_tts_batch call (shared codebook_eog / cur_num_gen / keep, voicecraft.py:1269-1325);
+// independent utterances are groups of size 1.
+// ---------------------------------------------------------------------------------------------------
+struct SlotState {
+    int x_len;          // text tokens
+    int seq_len;        // tokens already in the KV cache (text + audio columns)
+    int y_len;          // audio columns embedded so far == y_input.shape[1] in the reference
+    int group;          // group index
+    int member;         // index of this slot inside its group
+    int prev_token;     // silence bookkeeping (-1 = None)
+    int consec;         // consec_silence_count
+    int n_steps;        // sampling steps recorded in the token log
+    int forced;         // edit mode: number of upcoming forwards that feed a forced embedding (no sampling)
+    int active;         // 1 while the slot is open
+    int arrive;         // scratch: codebook rows finished in this step (last-CTA-done pattern)
+    int pad[5];
+};
+
+struct GroupState {
+    int mode;           // 0 = tts (voicecraft.py:1018-1067), 1 = edit (:718-787)
+    int size;           // number of member slots
+    int n_eog;          // how many codebooks have emitted their end token (always a prefix 0..n_eog-1)
+    int cur_num_gen;    // steps in the current span
+    int keep;           // batch mode: member index whose tokens are returned; -1 = undecided
+    int done;           // all spans finished
+    int spans_left;     // edit mode: masked spans still to generate after the current one
+    int trig_keep;      // scratch: 1 + max member index that triggered the end token in this step (0 = none)
+    int arrive;         // scratch: member slots finished in this step
+    int n_spans_done;
+    int first_slot;     // slot id of member 0 (members are consecutive slots)
+    int pad0;
+    int more_mask[8];   // edit mode: mask_embedding rows of the spans still to come
+    int span_ends[8];   // n_steps at which each span finished
+    int pad[4];
+};
+
+struct SamplingParams {
+    int top_k;
+    float top_p;
+    float temperature;
+    int stop_repetition;
+    int silence_tokens[8];
+    int n_silence;
+};
+
+struct ModelDims {
+    int d, H, hd, L, F, K, V, Vpad, Hh;   // Hh = predict_layer hidden (audio_vocab_size/2); Vpad = V rounded to 4
+    int n_text, empty_token, eog, eos, audio_pad, encodec_sr, max_n_spans;
+    int pe_len;
+};
+
+}  // namespace vcb

@@ -1,0 +1,493 @@
+"""B200-native drop-in for the inference surface of the reference's ``models/voicecraft.py``.
+
+Same constructor (``VoiceCraft(args)`` / ``VoiceCraft(config=dict)``), same ``state_dict`` keys, same
+``inference_tts`` / ``inference_tts_batch`` / ``inference`` signatures and return shapes
+(reference models/voicecraft.py:97-121, 561-573, 908-920, 1156-1169).  The module only *holds* the
+parameters; every inference call goes through libvcb200.so (hand-written sm_100a kernels: paged-KV
+attention, tcgen05 GEMMs, fused sampler).  There is no PyTorch / CPU fallback: without the extension or
+without a Blackwell GPU the calls raise.
+
+Random numbers: the reference samples with ``torch.multinomial(softmax(l), 1)``, which ATen evaluates as
+``argmax(softmax(l) / q)`` with ``q = empty_like(p).exponential_(1)`` from the device's global generator.
+This module draws exactly that ``q`` (same shape, once per sampling step) on the model's device and hands
+it to the fused sampler kernel, so the generator state advances as in the reference.  ``noise_fn`` can
+replace the draw (tests feed CPU-generator noise to compare against the CPU oracle).
+
+Out of scope (training): ``forward`` and ``prepare_mask_intervals`` raise NotImplementedError.
+"""
+import copy
+import ctypes as C
+import logging
+from argparse import Namespace
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .codebooks_patterns import DelayedPatternProvider
+
+try:  # same mixin as the reference (voicecraft.py:23, 89-95); optional so the hot path has no hard dependency
+    from huggingface_hub import PyTorchModelHubMixin
+    _HubBase = (PyTorchModelHubMixin,)
+    _HUB_KW = dict(library_name="voicecraft", repo_url="https://github.com/jasonppy/VoiceCraft", tags=["text-to-speech"])
+except Exception:  # pragma: no cover
+    _HubBase = ()
+    _HUB_KW = {}
+
+
+def sine_pe(length: int, dim: int) -> torch.Tensor:
+    """Sinusoidal table of SinePositionalEmbedding.extend_pe (embedding.py:67-92), fp32 [length, dim]."""
+    import math
+    pe = torch.zeros(length, dim)
+    position = torch.arange(0, length, dtype=torch.float32).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * -(math.log(10000.0) / dim))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter containers with the reference's attribute names (so state_dict keys match)
+# ---------------------------------------------------------------------------------------------------------
+class _TokenEmbedding(nn.Module):
+    def __init__(self, dim, vocab):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, dim)
+
+
+class _Alpha(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1))
+
+
+class _OutProj(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(d, d))
+        self.bias = nn.Parameter(torch.zeros(d))
+        nn.init.xavier_uniform_(self.weight)
+
+
+class _SelfAttn(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = _OutProj(d)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+
+
+class _Layer(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.self_attn = _SelfAttn(d)
+        self.linear1 = nn.Linear(d, 4 * d)
+        self.linear2 = nn.Linear(4 * d, d)
+        self.norm1 = nn.LayerNorm(d, eps=1e-5)
+        self.norm2 = nn.LayerNorm(d, eps=1e-5)
+
+
+class _Decoder(nn.Module):
+    def __init__(self, d, n_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([_Layer(d) for _ in range(n_layers)])
+        self.norm = nn.LayerNorm(d, eps=1e-5)
+
+
+class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
+    def __new__(cls, args: Optional[Namespace] = None, config: Optional[Dict] = None, **kwargs):
+        if args is not None:
+            if config is not None:
+                raise ValueError("Cannot provide both `args` and `config`.")
+            config = vars(args)
+        if _HubBase:
+            return super().__new__(cls, args=args, config=config, **kwargs)
+        return super().__new__(cls)
+
+    def __init__(self, args: Optional[Namespace] = None, config: Optional[Dict] = None):
+        super().__init__()
+        if args is None:
+            if config is None:
+                raise ValueError("Either `args` or `config` must be provided.")
+            args = Namespace(**config)
+        a = self.args = copy.copy(args)
+        self.pattern = DelayedPatternProvider(n_q=a.n_codebooks)
+        if not getattr(a, "special_first", False):
+            a.special_first = 0
+        if not getattr(a, "n_special", False):
+            a.n_special = 3
+        a.eos = getattr(a, "eos", -1)
+        K, d = a.n_codebooks, a.d_model
+        self.eog = nn.Parameter(torch.full((K, 1), a.eog, dtype=torch.long), requires_grad=False)
+        if a.eos > 0:
+            assert a.eos != a.audio_pad_token and a.eos != a.empty_token, a.eos
+            self.eos = nn.Parameter(torch.full((K, 1), a.eos, dtype=torch.long), requires_grad=False)
+        if isinstance(a.audio_vocab_size, str):
+            a.audio_vocab_size = eval(a.audio_vocab_size)
+        self.n_text_tokens = a.text_vocab_size + 1
+        assert a.text_pad_token == a.text_vocab_size
+        self.n_audio_tokens = [a.audio_vocab_size + a.n_special] * K
+        assert a.audio_vocab_size == a.empty_token, a.empty_token
+        assert a.eog == a.audio_vocab_size + 1, a.eog
+        assert a.audio_pad_token == a.audio_vocab_size + 2, a.audio_pad_token
+        assert getattr(a, "audio_embedding_dim", d) == d, "audio_embedding_dim must equal d_model (summed embeddings)"
+
+        self.text_embedding = _TokenEmbedding(d, self.n_text_tokens)
+        self.audio_embedding = nn.ModuleList([_TokenEmbedding(d, self.n_audio_tokens[k]) for k in range(K)])
+        self.mask_embedding = nn.Parameter(torch.randn(a.max_n_spans, d), requires_grad=True)
+        self.text_positional_embedding = _Alpha()
+        self.audio_positional_embedding = _Alpha()
+        self.decoder = _Decoder(d, a.num_decoder_layers)
+        self.predict_layer = nn.ModuleList([
+            nn.Sequential(nn.Linear(d, a.audio_vocab_size // 2), nn.GELU(),
+                          nn.Linear(a.audio_vocab_size // 2, self.n_audio_tokens[k])) for k in range(K)])
+
+        # engine configuration (see configure_engine)
+        self._eng = None
+        self._eng_key = None
+        self._eng_opts = dict(max_slots=8, max_seq_len=2048, max_new_tokens=4096, kv_dtype="bf16")
+        self.noise_fn = None          # optional: callable(shape, device) -> fp32 Exp(1) tensor on `device`
+        self.poll_every = 1
+        self.last_stats = {}
+        self.trace_logits = None      # set to a list to collect the raw logits [n*K, V] of every sampling step
+
+    # ------------------------------------------------------------------------------------------------
+    # training surface: out of scope for this build
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, batch):
+        raise NotImplementedError("training forward is out of scope of the B200 decode engine "
+                                  "(reference models/voicecraft.py:472-559)")
+
+    def prepare_mask_intervals(self, y_lens):
+        raise NotImplementedError("training-only helper (reference models/voicecraft.py:198-237)")
+
+    # ------------------------------------------------------------------------------------------------
+    # engine management
+    # ------------------------------------------------------------------------------------------------
+    def configure_engine(self, **opts):
+        """max_slots, max_seq_len, max_new_tokens, kv_dtype ('bf16' default | 'fp32').  Rebuilds lazily."""
+        for k in opts:
+            if k not in self._eng_opts:
+                raise KeyError(k)
+        self._eng_opts.update(opts)
+        self._drop_engine()
+
+    def _drop_engine(self):
+        if getattr(self, "_eng", None) is not None:
+            _lib.load().vcb_destroy(self._eng)
+        self._eng = None
+        self._eng_key = None
+
+    def __del__(self):
+        try:
+            self._drop_engine()
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        state_dict = {k: v for k, v in state_dict.items() if not k.startswith("accuracy_metrics")}
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._drop_engine()
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        if hasattr(self, "_eng"):
+            self._drop_engine()
+        return out
+
+    def _engine(self, need_slots=1, need_seq=0):
+        dev = self.mask_embedding.device
+        if dev.type != "cuda":
+            raise _lib.VcbError("VoiceCraft (B200) has no CPU path: move the model to a CUDA device (`.to('cuda')`)")
+        o = self._eng_opts
+        if need_slots > o["max_slots"] or need_seq > o["max_seq_len"]:
+            o["max_slots"] = max(o["max_slots"], need_slots)
+            o["max_seq_len"] = max(o["max_seq_len"], (need_seq + 255) // 256 * 256)
+            self._drop_engine()
+        key = (dev.index or 0, tuple(sorted(o.items())))
+        if self._eng is not None and self._eng_key == key:
+            return self._eng
+        self._drop_engine()
+        lib = _lib.load()
+        a = self.args
+        cfg = _lib.vcb_config(
+            d_model=a.d_model, nhead=a.nhead, num_layers=a.num_decoder_layers, n_codebooks=a.n_codebooks,
+            audio_vocab_size=a.audio_vocab_size, n_special=a.n_special, text_vocab_rows=self.n_text_tokens,
+            empty_token=a.empty_token, eog=a.eog, audio_pad_token=a.audio_pad_token, eos=a.eos if a.eos > 0 else -1,
+            encodec_sr=int(a.encodec_sr), max_n_spans=a.max_n_spans, max_slots=o["max_slots"],
+            max_seq_len=o["max_seq_len"], max_new_tokens=o["max_new_tokens"],
+            kv_dtype=1 if o["kv_dtype"] == "fp32" else 0, device=dev.index or 0)
+        h = C.c_void_p()
+        _lib.check(lib.vcb_create(C.byref(cfg), C.byref(h)))
+        try:
+            with torch.cuda.device(dev):
+                for k, v in self.state_dict().items():
+                    if not v.is_floating_point():
+                        continue
+                    t = v.detach().to(device=dev, dtype=torch.float32).contiguous()
+                    shape = (C.c_int64 * max(t.dim(), 1))(*t.shape) if t.dim() else (C.c_int64 * 1)(1)
+                    _lib.check(lib.vcb_load_weight(h, k.encode(), t.data_ptr(), shape, max(t.dim(), 1), 1))
+                pe = sine_pe(max(4000, o["max_seq_len"]), a.d_model).to(dev)
+                _lib.check(lib.vcb_load_pe(h, pe.data_ptr(), pe.shape[0], 1))
+                _lib.check(lib.vcb_finalize_weights(h))
+        except Exception:
+            lib.vcb_destroy(h)
+            raise
+        self._eng, self._eng_key = h, key
+        return h
+
+    # ------------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------------
+    def _sampling(self, top_k, top_p, temperature, stop_repetition, silence_tokens):
+        sp = _lib.vcb_sampling(top_k=int(top_k), top_p=float(top_p), temperature=float(temperature),
+                               stop_repetition=int(stop_repetition), n_silence=min(len(silence_tokens), 8))
+        for i, t in enumerate(list(silence_tokens)[:8]):
+            sp.silence_tokens[i] = int(t)
+        return sp
+
+    def _draw_noise(self, buf):
+        """Exp(1) noise with the call shape of the reference's multinomial draw (in place on a persistent buffer)."""
+        if self.noise_fn is not None:
+            q = self.noise_fn(tuple(buf.shape), buf.device)
+            buf.copy_(q.to(device=buf.device, dtype=torch.float32))
+        else:
+            buf.exponential_(1)
+        return buf
+
+    def shift(self, rearranged_y):
+        """Delay every segment with the codebook pattern (reference voicecraft.py:254-262)."""
+        shifted_y, patterns = [], []
+        for segs in rearranged_y:
+            pats = [self.pattern.get_pattern(s.shape[1]) for s in segs]
+            out = [p.build_pattern_sequence(z=s.unsqueeze(0).contiguous(), special_token=self.args.empty_token,
+                                            keep_only_valid_steps=False) for p, s in zip(pats, segs)]
+            shifted_y.append([o[0].squeeze(0) for o in out])
+            patterns.append(pats)
+        return shifted_y, patterns
+
+    def _run(self, eng, slots, n_rows, sp, stream, max_steps=None):
+        """prefill is done; run sample / decode_step until every listed slot's group is done."""
+        lib = _lib.load()
+        a = self.args
+        dev = self.mask_embedding.device
+        K, V = a.n_codebooks, self.n_audio_tokens[0]
+        n = len(slots)
+        c_slots = (C.c_int32 * n)(*slots)
+        noise = torch.empty(n_rows * K, V, device=dev, dtype=torch.float32)
+        status = (_lib.vcb_status * n)()
+        def trace():
+            if self.trace_logits is not None:
+                t = torch.empty(n_rows * K, V, device=dev, dtype=torch.float32)
+                _lib.check(lib.vcb_debug_logits(eng, t.data_ptr(), n_rows * K))
+                self.trace_logits.append(t)
+        self._draw_noise(noise)
+        _lib.check(lib.vcb_sample(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
+        trace()
+        steps = 1
+        while True:
+            _lib.check(lib.vcb_poll(eng, c_slots, n, status, stream))
+            if all(s.done for s in status):
+                break
+            if max_steps is not None and steps >= max_steps:
+                break
+            forced = any(s.forced for s in status)
+            if not forced:                               # forced hand-over steps consume no random numbers
+                self._draw_noise(noise)
+            _lib.check(lib.vcb_decode_step(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
+            if not forced:
+                trace()
+            steps += 1
+        return status
+
+    def _read_rows(self, eng, slot, n_steps, stream):
+        K = self.args.n_codebooks
+        buf = (C.c_int32 * (n_steps * K))()
+        _lib.check(_lib.load().vcb_read_tokens(eng, slot, buf, n_steps, stream))
+        return np.frombuffer(buf, dtype=np.int32).reshape(n_steps, K).astype(np.int64)
+
+    @staticmethod
+    def _undelay(rows: np.ndarray, K: int) -> np.ndarray:
+        """rows [n,K] (delayed, as sampled) -> [K, n-K]   (reference voicecraft.py:1126-1137)."""
+        n = rows.shape[0]
+        return np.stack([rows[k: n - (K - k), k] for k in range(K)], axis=0)
+
+    # ------------------------------------------------------------------------------------------------
+    # inference_tts  (reference voicecraft.py:908-1153)
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def inference_tts(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, top_k: int = -100,
+                      top_p: float = 1.0, temperature: float = 1.0, stop_repetition: int = 3, kvcache: int = 1,
+                      silence_tokens: List[int] = [1388, 1898, 131], *kargs):
+        res, gen = self._tts_impl(x, x_lens, y, top_k, top_p, temperature, stop_repetition, silence_tokens, 1)
+        return res, gen
+
+    @torch.no_grad()
+    def inference_tts_batch(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, top_k: int = -100,
+                            top_p: float = 1.0, temperature: float = 1.0, stop_repetition: int = 3, kvcache: int = 1,
+                            batch_size: int = 5, silence_tokens: List[int] = [1388, 1898, 131], *kargs):
+        """Best-of-N: the first sample to end wins (reference voicecraft.py:1156-1439)."""
+        return self._tts_impl(x, x_lens, y, top_k, top_p, temperature, stop_repetition, silence_tokens, batch_size)
+
+    def _tts_impl(self, x, x_lens, y, top_k, top_p, temperature, stop_repetition, silence_tokens, n_copies):
+        a = self.args
+        K = a.n_codebooks
+        assert x.ndim == 2, x.shape
+        assert x_lens.ndim == 1, x_lens.shape
+        assert y.ndim == 3, y.shape
+        dev = self.mask_embedding.device
+        x = x.to(dev)
+        y = y.to(dev)
+        if a.special_first:
+            y = y + int(a.n_special)
+        y = y.transpose(2, 1)                                     # [1,T,K] -> [1,K,T]
+        assert y.shape[0] == 1 and y.shape[1] == K, y.shape
+        logging.info(f"silence tokens: {silence_tokens}, note that if you are not using the pretrained encodec "
+                     f"6f79c6a8, make sure you specified it yourself, rather than using the default")
+        shifted, _ = self.shift([[y[0].long()]])
+        prompt = shifted[0][0][:, : -(K - 1)] if K > 1 else shifted[0][0]     # voicecraft.py:967
+        y_tok = prompt.transpose(1, 0).contiguous()                           # [T+1, K]
+        x_len, y_len = int(x.shape[1]), int(y_tok.shape[0])
+        cap = x_len * (int(a.encodec_sr) // 5)
+        need_seq = x_len + max(y_len, cap + 1) + K + 8
+        eng = self._engine(need_slots=n_copies, need_seq=need_seq)
+        lib = _lib.load()
+        x_ids = x[0].long().contiguous()
+        sp = self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            P = _lib.vcb_prompt(slot=0, n_copies=n_copies, mode=0, x_len=x_len, text_ids_dev=x_ids.data_ptr(),
+                                y_len=y_len, y_tokens_dev=y_tok.data_ptr(), mask_rows_dev=None, n_more_spans=0)
+            try:
+                _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))
+                slots = list(range(n_copies))
+                status = self._run(eng, slots, n_copies, sp, stream)
+                keep = status[0].keep if n_copies > 1 else 0
+                rows = self._read_rows(eng, keep, status[keep].n_steps, stream)
+            finally:
+                lib.vcb_release(eng, 0, n_copies)
+        gen = torch.from_numpy(self._undelay(rows, K)).to(dev)
+        res = torch.cat([y[0].long(), gen], dim=1).unsqueeze(0)
+        expected = y.shape[2] + rows.shape[0] - K
+        assert res.shape == torch.Size((1, K, expected)), f"res.shape: {res.shape}, expected_y_len: {expected}"
+        if a.special_first:
+            res = res - int(a.n_special)
+            gen = gen - int(a.n_special)
+        self.last_stats = dict(steps=int(rows.shape[0]), keep=int(keep))
+        return res, gen.unsqueeze(0)
+
+    # ------------------------------------------------------------------------------------------------
+    # speech editing  (reference voicecraft.py:561-906)
+    # ------------------------------------------------------------------------------------------------
+    def _edit_prompt(self, y, spans):
+        """Segment / placeholder layout of voicecraft.py:239-320, 615-683 as integer index tables.
+
+        y [K,T] (device).  Returns (tokens [T',K] int64 device, mask_rows int32 [T'], more_mask_rows, non_mask)."""
+        a = self.args
+        K, T = y.shape
+        M = len(spans)
+        reduced_eog = getattr(a, "reduced_eog", 0)
+        starts = [s for s, _ in spans] + [T]
+        ends = [0] + [e for _, e in spans]
+        non_mask = list(zip(ends, starts))
+        # (source interval, end token or None) for every segment, non-masked first then masked
+        segs = []
+        for i, (s0, s1) in enumerate(non_mask):
+            last = i == len(non_mask) - 1
+            if a.eos > 0:
+                assert reduced_eog
+                tail = a.eos if last else None
+            elif reduced_eog:
+                tail = a.eog if last else None
+            else:
+                tail = a.eog
+            segs.append((s0, s1, tail))
+        for (s0, s1) in spans:
+            segs.append((s0, s1, a.eog))
+        assert not getattr(a, "shuffle_mask_embedding", 0), "shuffle_mask_embedding is a training-time option"
+        vals = list(range(a.max_n_spans))[:M]
+        mask_val = vals + vals
+        # column table: src[k, c] >= 0 -> y[k, src]; otherwise -(token+1)
+        cols_src = []
+        mask_rows = []
+        for j, (s0, s1, tail) in enumerate(segs):
+            n_src = (s1 - s0) + (1 if tail is not None else 0)
+            blk = np.full((K, n_src + K), -(a.empty_token + 1), dtype=np.int64)
+            for k in range(K):
+                blk[k, 1 + k: 1 + k + (s1 - s0)] = np.arange(s0, s1)
+                if tail is not None:
+                    blk[k, 1 + k + (s1 - s0)] = -(tail + 1)
+            cols_src.append(blk)
+            mask_rows += [-1] * blk.shape[1]
+            if j < len(segs) - 1:
+                cols_src.append(np.full((K, 1), -(a.eog + 1), dtype=np.int64))    # placeholder column (:264-288)
+                mask_rows.append(mask_val[j])
+        src = np.concatenate(cols_src, axis=1)
+        # cut right after placeholder M plus the first (all-empty) column of the first masked segment (:672-679)
+        ph = [i for i, m in enumerate(mask_rows) if m >= 0]
+        cut = ph[M] + 2
+        src, mask_rows = src[:, :cut], mask_rows[:cut]
+        src_t = torch.from_numpy(src).to(y.device)
+        tok = torch.where(src_t >= 0, torch.gather(y, 1, src_t.clamp(min=0)), -(src_t + 1))
+        return (tok.transpose(1, 0).contiguous(), torch.tensor(mask_rows, dtype=torch.int32, device=y.device),
+                mask_val[M + 1:], non_mask)
+
+    @torch.no_grad()
+    def inference(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, mask_interval: torch.Tensor,
+                  top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0, stop_repetition: int = -1,
+                  kvcache: int = 1, silence_tokens: List[int] = [1388, 1898, 131]) -> torch.Tensor:
+        a = self.args
+        K = a.n_codebooks
+        assert x.ndim == 2, x.shape
+        assert x_lens.ndim == 1, x_lens.shape
+        assert y.ndim == 3, y.shape
+        dev = self.mask_embedding.device
+        x = x.to(dev)
+        y = y.to(dev)
+        if a.special_first:
+            y = y + int(a.n_special)
+        y = y.transpose(2, 1)
+        assert y.shape[0] == 1 and y.shape[1] == K, y.shape
+        assert mask_interval.shape == torch.Size((1, mask_interval.shape[1], 2)), mask_interval
+        spans = [(int(s), int(e)) for s, e in mask_interval[0].tolist()]
+        logging.info(f"silence tokens: {silence_tokens}, note that if you are not using the pretrained encodec "
+                     f"6f79c6a8, make sure you specified it yourself, rather than using the default")
+        y0 = y[0].long().contiguous()
+        y_tok, mask_rows, more_vals, non_mask = self._edit_prompt(y0, spans)
+        x_len, y_len = int(x.shape[1]), int(y_tok.shape[0])
+        cap = x_len * 10
+        need_seq = x_len + max(y_len, cap + 1) + (K + 3) * (len(spans) + 1) + 8
+        eng = self._engine(need_slots=1, need_seq=need_seq)
+        lib = _lib.load()
+        x_ids = x[0].long().contiguous()
+        sp = self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            P = _lib.vcb_prompt(slot=0, n_copies=1, mode=1, x_len=x_len, text_ids_dev=x_ids.data_ptr(), y_len=y_len,
+                                y_tokens_dev=y_tok.data_ptr(), mask_rows_dev=mask_rows.data_ptr(),
+                                n_more_spans=len(more_vals))
+            for i, v in enumerate(more_vals):
+                P.more_mask_rows[i] = int(v)
+            try:
+                _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))
+                status = self._run(eng, [0], 1, sp, stream)
+                rows = self._read_rows(eng, 0, status[0].n_steps, stream)
+                ends = [status[0].span_ends[i] for i in range(status[0].n_spans_done)]
+            finally:
+                lib.vcb_release(eng, 0, 1)
+        assert len(ends) == len(spans), f"len(generated): {len(ends)}, num_mask: {len(spans)}"
+        pieces, lo = [], 0
+        for (s0, s1), hi in zip(non_mask, ends):
+            pieces.append(y0[:, s0:s1])
+            pieces.append(torch.from_numpy(self._undelay(rows[lo:hi], K)).to(dev))
+            lo = hi
+        pieces.append(y0[:, non_mask[-1][0]: non_mask[-1][1]])
+        res = torch.cat(pieces, dim=1).unsqueeze(0)
+        if a.special_first:
+            res = res - int(a.n_special)
+        self.last_stats = dict(steps=int(rows.shape[0]))
+        return res
