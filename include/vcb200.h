@@ -105,7 +105,10 @@ int vcb_release(vcb_engine* e, int32_t slot, int32_t n_copies);
 int vcb_debug_logits(vcb_engine* e, float* out_dev, int32_t n_rows);   /* last sampled logits [n*K][V] (pre-edit) */
 int vcb_debug_gemm(const float* W_dev /*[N][K]*/, const float* X_dev /*[B][K]*/, float* out_dev /*[B][N]*/, int32_t N,
                    int32_t K, int32_t B, int32_t splits /*<=0: auto*/, int32_t simt);
-int vcb_set_option(vcb_engine* e, const char* name, int32_t value);   /* "gemm_simt", "pdl", "graphs" */
+int vcb_set_option(vcb_engine* e, const char* name, int32_t value);   /* "gemm_simt", "pdl", "profile" */
+/* profile mode: summed device ms and launch counts per kernel class since the last read
+ * (0 gemm, 1 attention, 2 layernorm/reduce, 3 bias/act/qkv finish, 4 sampler, 5 misc) */
+int vcb_profile_read(vcb_engine* e, double* ms_by_class, int64_t* count_by_class, int32_t n_classes);
 int64_t vcb_counter(vcb_engine* e, const char* name);                 /* "launches", "kv_bytes", ... */
 
 /* ---- delayed codebook pattern on the device: Pattern.build_pattern_sequence

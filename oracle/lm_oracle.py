@@ -341,7 +341,8 @@ class OracleLM:
     # -- inference_tts_batch (best-of-N, first EOG wins) --------------------------------
     @torch.no_grad()
     def inference_tts_batch(self, x, x_lens, y, top_k=-100, top_p=1.0, temperature=1.0, stop_repetition=3,
-                            kvcache=1, batch_size=5, silence_tokens=(1388, 1898, 131), noise_fn=None):
+                            kvcache=1, batch_size=5, silence_tokens=(1388, 1898, 131), noise_fn=None,
+                            max_steps=None, on_step=None):
         c = self.c
         K, Bn = c.n_codebooks, batch_size
         noise_fn = noise_fn or default_noise
@@ -413,8 +414,12 @@ class OracleLM:
                 kept_rows.append(s[keep].squeeze(-1))
             else:
                 kept_rows.append(s[keep].squeeze(-1))
+            if on_step is not None:
+                on_step(cur)
             if sum(eog) == K:
                 break
+            if max_steps is not None and cur >= max_steps and sum(eog) == 0:
+                return None, None            # bounded timing sample (bench.py cpu_baseline), no result assembled
             step_emb = torch.stack([F.embedding(s[:, k], self.sd[f"audio_embedding.{k}.word_embeddings.weight"])
                                     for k in range(K)], dim=1).sum(dim=1)            # [B,1,D]
             emb = torch.cat([emb, step_emb], dim=1)

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "vcb_debug_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "vcb_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vcb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "vcb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "vcb_counter": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "vcb_delay_pattern": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
 }

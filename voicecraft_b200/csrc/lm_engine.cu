@@ -91,8 +91,30 @@ struct vcb_engine {
     size_t h_stage_ints = 0;
     cudaEvent_t stage_ev = nullptr;
 
-    int opt_simt = 0, opt_pdl = 0;
+    int opt_simt = 0, opt_pdl = 0, opt_profile = 0;
     int64_t n_launches = 0;
+    // profile mode: CUDA events around every launch, by kernel class
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+
+enum { PC_GEMM = 0, PC_ATTN = 1, PC_LN = 2, PC_FINISH = 3, PC_SAMPLER = 4, PC_MISC = 5, PC_N = 6 };
+
+struct ProfScope {
+    vcb_engine* e; cudaStream_t st; int idx = -1;
+    ProfScope(vcb_engine* e_, int cls, cudaStream_t st_) : e(e_), st(st_) {
+        if (!e->opt_profile) return;
+        vcb_engine::ProfRec r{cls, e->get_event(), e->get_event()};
+        cudaEventRecord(r.a, st);
+        e->prof.push_back(r);
+        idx = static_cast<int>(e->prof.size()) - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof[idx].b, st); }
 };
 
 namespace {
@@ -191,6 +213,7 @@ int run_gemm(vcb_engine* e, const Matrix& W, const CUtensorMap* tmB, const __nv_
     }
     *splits_out = g.splits;
     LAUNCH_COUNT(e);
+    ProfScope ps(e, PC_GEMM, st);
     return gemm_launch(g, st);
 }
 
@@ -198,6 +221,7 @@ template <typename KVT>
 int launch_attn_t(vcb_engine* e, const Layer& Ly, int rows, int bpad, cudaStream_t st) {
     const ModelDims& m = e->m;
     const float scale = 1.0f / sqrtf(static_cast<float>(m.hd));
+    ProfScope ps(e, PC_ATTN, st);
     if (m.hd == 128) {
         using L = AttSmem<KVT, 128>;
         static bool set = false;
@@ -229,6 +253,7 @@ int launch_attn_t(vcb_engine* e, const Layer& Ly, int rows, int bpad, cudaStream
 int launch_ln(vcb_engine* e, const float* x_in, const int* src_index, float* x_out, int nsplit, int ldp, int bpad,
               const float* bias, const float* g, const float* b, int rows, cudaStream_t st) {
     const int d = e->m.d;
+    ProfScope ps(e, PC_LN, st);
     if (d <= 2048)
         ln_rows_kernel<8><<<rows, 256, 0, st>>>(x_in, src_index, x_out, e->partial, nsplit, ldp, bpad, bias, g, b,
                                                  e->act_d, d, d, 1e-5f);
@@ -257,6 +282,8 @@ int forward_rows(vcb_engine* e, int rows, cudaStream_t st) {
         int sp;
         if (run_gemm(e, Ly.qkv, &e->tm_act_d[bi], e->act_d, m.d, bpad, rows, 0, m.d, &sp, st)) return -1;
         const int ldp_qkv = (3 * m.d + 3) & ~3;
+        {
+        ProfScope ps(e, PC_FINISH, st);
         if (e->kv_fp32)
             qkv_finish_kernel<float><<<rows, 256, 0, st>>>(e->partial, sp, ldp_qkv, bpad, Ly.b_qkv, e->qbuf,
                                                           static_cast<float*>(Ly.kpool), static_cast<float*>(Ly.vpool),
@@ -267,6 +294,7 @@ int forward_rows(vcb_engine* e, int rows, cudaStream_t st) {
                 e->partial, sp, ldp_qkv, bpad, Ly.b_qkv, e->qbuf, static_cast<__nv_bfloat16*>(Ly.kpool),
                 static_cast<__nv_bfloat16*>(Ly.vpool), e->page_table, e->max_pages_per_slot, e->cur_slot, e->cur_pos,
                 m.d, m.H, m.hd);
+        }
         VCB_CUDA_OK(cudaGetLastError());
         LAUNCH_COUNT(e);
         if (e->kv_fp32 ? launch_attn_t<float>(e, Ly, rows, bpad, st) : launch_attn_t<__nv_bfloat16>(e, Ly, rows, bpad, st))
@@ -276,8 +304,11 @@ int forward_rows(vcb_engine* e, int rows, cudaStream_t st) {
         if (launch_ln(e, e->x_rows, nullptr, e->x_rows, sp, (m.d + 3) & ~3, bpad, Ly.b_out, Ly.ln2_g, Ly.ln2_b, rows, st))
             return -1;
         if (run_gemm(e, Ly.ff1, &e->tm_act_d[bi], e->act_d, m.d, bpad, rows, 0, m.d, &sp, st)) return -1;
-        bias_act_kernel<<<dim3((m.F + 255) / 256, rows), 256, 0, st>>>(e->partial, sp, (m.F + 3) & ~3, bpad, Ly.b_ff1,
-                                                                       m.F, 1, e->act_f, m.F);
+        {
+            ProfScope ps(e, PC_FINISH, st);
+            bias_act_kernel<<<dim3((m.F + 255) / 256, rows), 256, 0, st>>>(e->partial, sp, (m.F + 3) & ~3, bpad,
+                                                                           Ly.b_ff1, m.F, 1, e->act_f, m.F);
+        }
         VCB_CUDA_OK(cudaGetLastError());
         LAUNCH_COUNT(e);
         if (run_gemm(e, Ly.ff2, &e->tm_act_f[bi], e->act_f, m.F, bpad, rows, 0, m.F, &sp, st)) return -1;
@@ -285,8 +316,11 @@ int forward_rows(vcb_engine* e, int rows, cudaStream_t st) {
         ldp_prev = (m.d + 3) & ~3;
         bias_prev = Ly.b_ff2;
     }
-    reduce_rows_kernel<<<rows, 256, 0, st>>>(e->x_rows, e->partial, sp_prev, ldp_prev, bpad, bias_prev, e->h_slot,
-                                             e->cur_last, m.d);
+    {
+        ProfScope ps(e, PC_LN, st);
+        reduce_rows_kernel<<<rows, 256, 0, st>>>(e->x_rows, e->partial, sp_prev, ldp_prev, bpad, bias_prev, e->h_slot,
+                                                 e->cur_last, m.d);
+    }
     VCB_CUDA_OK(cudaGetLastError());
     LAUNCH_COUNT(e);
     return 0;
@@ -315,8 +349,11 @@ int sample_rows(vcb_engine* e, int n, const float* noise, const vcb_sampling* sp
     int s1;
     if (run_gemm(e, e->h1, &e->tm_act_d[bi], e->act_d, m.d, bpad, n, 0, m.d, &s1, st)) return -1;
     const int KH = m.K * m.Hh;
-    bias_act_kernel<<<dim3((KH + 255) / 256, n), 256, 0, st>>>(e->partial, s1, (KH + 3) & ~3, bpad, e->b_h1, KH, 2,
-                                                               e->act_h, KH);
+    {
+        ProfScope ps(e, PC_FINISH, st);
+        bias_act_kernel<<<dim3((KH + 255) / 256, n), 256, 0, st>>>(e->partial, s1, (KH + 3) & ~3, bpad, e->b_h1, KH, 2,
+                                                                   e->act_h, KH);
+    }
     VCB_CUDA_OK(cudaGetLastError());
     LAUNCH_COUNT(e);
     // K second-stage GEMMs write disjoint column blocks [k*Vpad, (k+1)*Vpad) of one logits partial buffer
@@ -346,6 +383,7 @@ int sample_rows(vcb_engine* e, int n, const float* noise, const vcb_sampling* sp
         g.pdl = e->opt_pdl;
         g.simt = e->opt_simt;
         LAUNCH_COUNT(e);
+        ProfScope ps(e, PC_GEMM, st);
         if (gemm_launch(g, st)) return -1;
     }
     SamplerArgs a;
@@ -382,6 +420,7 @@ int sample_rows(vcb_engine* e, int n, const float* noise, const vcb_sampling* sp
     a.sp.n_silence = std::min(sp->n_silence, 8);
     for (int i = 0; i < 8; ++i) a.sp.silence_tokens[i] = sp->silence_tokens[i];
     const size_t dyn = SAMP_SORT_N * 8 + static_cast<size_t>(m.V) * 4;
+    ProfScope ps(e, PC_SAMPLER, st);
     sampler_kernel<<<n * m.K, SAMP_THREADS, dyn, st>>>(a);
     VCB_CUDA_OK(cudaGetLastError());
     LAUNCH_COUNT(e);
@@ -774,8 +813,11 @@ int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float*
     }
     VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
     if (upload_slots(e, slots, n, st)) return -1;
-    step_prep_kernel<<<n, 256, 0, st>>>(e->d_slots, n, e->st, e->gr, e->row_slot, e->row_pos, e->row_last, e->x_slot,
-                                        e->x_rows, e->m.d);
+    {
+        ProfScope ps(e, PC_MISC, st);
+        step_prep_kernel<<<n, 256, 0, st>>>(e->d_slots, n, e->st, e->gr, e->row_slot, e->row_pos, e->row_last, e->x_slot,
+                                            e->x_rows, e->m.d);
+    }
     VCB_CUDA_OK(cudaGetLastError());
     LAUNCH_COUNT(e);
     e->cur_slot = e->row_slot;
@@ -901,8 +943,25 @@ int vcb_debug_gemm(const float* W_dev, const float* X_dev, float* out_dev, int32
     return 0;
 }
 
+// Profile mode (vcb_set_option("profile", 1)): per kernel class, summed device time [ms] and launch count of
+// everything recorded since the last read.  Synchronises the device.
+int vcb_profile_read(vcb_engine* e, double* ms_by_class, int64_t* count_by_class, int32_t n_classes) {
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0; count_by_class[i] = 0; }
+    for (auto& r : e->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        if (r.cls < n_classes) { ms_by_class[r.cls] += ms; count_by_class[r.cls] += 1; }
+        e->ev_pool.push_back(r.a);
+        e->ev_pool.push_back(r.b);
+    }
+    e->prof.clear();
+    return 0;
+}
+
 int vcb_set_option(vcb_engine* e, const char* name, int32_t value) {
     if (!strcmp(name, "gemm_simt")) e->opt_simt = value;
+    else if (!strcmp(name, "profile")) e->opt_profile = value;
     else if (!strcmp(name, "pdl")) e->opt_pdl = value;
     else {
         set_error("unknown option %s", name);

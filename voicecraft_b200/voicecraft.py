@@ -491,3 +491,121 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             res = res - int(a.n_special)
         self.last_stats = dict(steps=int(rows.shape[0]))
         return res
+
+    # ------------------------------------------------------------------------------------------------
+    # driver-level batching of INDEPENDENT utterances (BASELINE config 2).
+    # Not a reference API: the reference decodes one utterance per call.  Each utterance keeps its own
+    # state machine; one Exp(1) draw of shape [B*K, V] per step feeds all of them.
+    # ------------------------------------------------------------------------------------------------
+    def open_tts_session(self, xs, ys, top_k=-100, top_p=1.0, temperature=1.0, stop_repetition=3,
+                         silence_tokens=(1388, 1898, 131)):
+        """xs: list of [1,L] int64, ys: list of [1,T,K] int64 (any device).  Prefills every utterance (one packed,
+        chunked pass) and returns a DecodeSession whose .step() runs one decode step for all of them."""
+        return DecodeSession(self, xs, ys, self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens))
+
+    @torch.no_grad()
+    def inference_tts_many(self, xs, ys, poll_every: int = 8, **kw):
+        """Returns a list of (res [1,K,T+G], gen [1,K,G]) like inference_tts, one per utterance."""
+        sess = self.open_tts_session(xs, ys, **kw)
+        try:
+            sess.sample()
+            while True:
+                if sess.steps % poll_every == 0 and sess.all_done():
+                    break
+                sess.step()
+            return sess.results()
+        finally:
+            sess.close()
+
+
+class DecodeSession:
+    """A batch of independent TTS utterances resident in the engine (slots 0..B-1)."""
+
+    def __init__(self, model: "VoiceCraft", xs, ys, sp):
+        a = model.args
+        K = a.n_codebooks
+        dev = model.mask_embedding.device
+        self.model, self.sp, self.dev, self.K = model, sp, dev, K
+        self.B = len(xs)
+        self.lib = _lib.load()
+        prompts, keep_alive, need_seq = [], [], 0
+        self.y0 = []
+        for x, y in zip(xs, ys):
+            assert x.ndim == 2 and y.ndim == 3 and y.shape[2] == K
+            x = x.to(dev, non_blocking=True)
+            y = y.to(dev, non_blocking=True)
+            if a.special_first:
+                y = y + int(a.n_special)
+            yk = y.transpose(2, 1)[0].long()
+            shifted, _ = model.shift([[yk]])
+            prompt = shifted[0][0][:, : -(K - 1)] if K > 1 else shifted[0][0]
+            y_tok = prompt.transpose(1, 0).contiguous()
+            x_ids = x[0].long().contiguous()
+            keep_alive += [y_tok, x_ids]
+            self.y0.append(yk)
+            cap = int(x.shape[1]) * (int(a.encodec_sr) // 5)
+            need_seq = max(need_seq, int(x.shape[1]) + max(int(y_tok.shape[0]), cap + 1) + K + 8)
+            prompts.append((int(x.shape[1]), x_ids, int(y_tok.shape[0]), y_tok))
+        self.eng = model._engine(need_slots=self.B, need_seq=need_seq)
+        self.V = model.n_audio_tokens[0]
+        P = (_lib.vcb_prompt * self.B)()
+        for i, (xl, x_ids, yl, y_tok) in enumerate(prompts):
+            P[i] = _lib.vcb_prompt(slot=i, n_copies=1, mode=0, x_len=xl, text_ids_dev=x_ids.data_ptr(), y_len=yl,
+                                   y_tokens_dev=y_tok.data_ptr(), mask_rows_dev=None, n_more_spans=0)
+        self.c_slots = (C.c_int32 * self.B)(*range(self.B))
+        self.status = (_lib.vcb_status * self.B)()
+        self.noise = torch.empty(self.B * K, self.V, device=dev, dtype=torch.float32)
+        self.steps = 0
+        self._open = True
+        with torch.cuda.device(dev):
+            self.stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.vcb_prefill(self.eng, P, self.B, self.stream))
+        self._keep_alive = keep_alive
+
+    def sample(self):
+        """first sampling step (on the prefill's last hidden states)"""
+        self.model._draw_noise(self.noise)
+        _lib.check(self.lib.vcb_sample(self.eng, self.c_slots, self.B, self.noise.data_ptr(), C.byref(self.sp), self.stream))
+        self.steps += 1
+
+    def step(self):
+        self.model._draw_noise(self.noise)
+        _lib.check(self.lib.vcb_decode_step(self.eng, self.c_slots, self.B, self.noise.data_ptr(), C.byref(self.sp),
+                                            self.stream))
+        self.steps += 1
+
+    def poll(self):
+        _lib.check(self.lib.vcb_poll(self.eng, self.c_slots, self.B, self.status, self.stream))
+        return self.status
+
+    def all_done(self):
+        return all(s.done for s in self.poll())
+
+    def raw_tokens(self, i):
+        """delayed token rows [n_steps, K] of utterance i (host numpy)"""
+        st = self.poll()
+        return self.model._read_rows(self.eng, i, st[i].n_steps, self.stream)
+
+    def results(self):
+        out = []
+        a = self.model.args
+        st = self.poll()
+        for i in range(self.B):
+            rows = self.model._read_rows(self.eng, i, st[i].n_steps, self.stream)
+            if st[i].done:
+                gen = torch.from_numpy(VoiceCraft._undelay(rows, self.K)).to(self.dev)
+            else:       # truncated session: drop the still-delayed tail
+                n = rows.shape[0]
+                gen = torch.from_numpy(np.stack([rows[k: n - (self.K - 1) + k, k] for k in range(self.K)], 0)).to(self.dev) \
+                    if n >= self.K else torch.zeros(self.K, 0, dtype=torch.long, device=self.dev)
+            res = torch.cat([self.y0[i], gen], dim=1).unsqueeze(0)
+            if a.special_first:
+                res, gen = res - int(a.n_special), gen - int(a.n_special)
+            out.append((res, gen.unsqueeze(0)))
+        return out
+
+    def close(self):
+        if self._open:
+            for i in range(self.B):
+                self.lib.vcb_release(self.eng, i, 1)
+            self._open = False
