@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--text-len", type=int, default=80)
     ap.add_argument("--prompt", type=int, default=150)
     ap.add_argument("--kv", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-steps", type=int, default=12, help="decode steps of the bounded CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=4, help="decode steps of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -117,11 +117,24 @@ def algorithmic_bytes(cfg, B, S_mean, kv_bytes):
     return W, B * S_mean * kv_tok, B * kv_tok
 
 
+def host_threads():
+    """Usable host cores: affinity mask, cgroup CPU quota, capped at 64 (fp32 GEMV-like steps stop scaling earlier)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    env = os.environ.get("BENCH_CPU_THREADS")
+    return int(env) if env else max(1, min(n, 64))
+
+
 def cpu_baseline(args, cfg, sd, utts, steps, threads=None):
     """The oracle port of the reference's own batched decode (inference_tts_batch, B copies of one prompt ==
     the compute of B independent utterances of that length) timed on the host cores, bounded sample."""
     from oracle import lm_oracle
-    threads = threads or os.cpu_count()
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     oracle = lm_oracle.OracleLM(cfg, sd)
     x, x_lens, y = utts[0]
@@ -255,8 +268,8 @@ def main():
             cnt = (C.c_int64 * 6)()
             lib.vcb_profile_read(eng, msb, cnt, 6)
             lib.vcb_set_option(eng, b"profile", 0)
-            names = ["gemm_w_xT_splitk(tcgen05)", "attn_rows_kernel(paged KV, TMA bulk)", "ln_rows/reduce", "bias_act/qkv_finish",
-                     "sampler_kernel", "step_prep"]
+            names = ["gemm_w_xT_cluster(tcgen05, cluster split-K)", "attn_rows_kernel(paged KV, TMA bulk, split ctx)",
+                     "ln_rows_kernel", "(unused)", "sampler_kernel", "step_prep"]
             total = sum(msb)
             shares = {names[i]: {"ms_per_step": msb[i] / nprof, "launches_per_step": cnt[i] / nprof, "share": msb[i] / total}
                       for i in range(6)}

@@ -105,6 +105,12 @@ int vcb_release(vcb_engine* e, int32_t slot, int32_t n_copies);
 int vcb_debug_logits(vcb_engine* e, float* out_dev, int32_t n_rows);   /* last sampled logits [n*K][V] (pre-edit) */
 int vcb_debug_gemm(const float* W_dev /*[N][K]*/, const float* X_dev /*[B][K]*/, float* out_dev /*[B][N]*/, int32_t N,
                    int32_t K, int32_t B, int32_t splits /*<=0: auto*/, int32_t simt);
+/* debug timeline: enable=1 starts recording (tag, globaltimer ns) pairs from CTA 0 of each kernel; enable=0 stops and
+ * copies up to max_records pairs to out_host */
+int vcb_timeline(int32_t enable, uint64_t* out_host, int32_t max_records, int32_t* n_out);
+/* micro-benchmark of the GEMM kernel alone (HBM-resident weights): average microseconds per launch */
+int vcb_bench_gemm(int32_t N, int32_t K, int32_t B, int32_t splits, int32_t stages, int32_t pdl, int32_t iters,
+                   int32_t ncopies, float* us_out);
 int vcb_set_option(vcb_engine* e, const char* name, int32_t value);   /* "gemm_simt", "pdl", "profile" */
 /* profile mode: summed device ms and launch counts per kernel class since the last read
  * (0 gemm, 1 attention, 2 layernorm/reduce, 3 bias/act/qkv finish, 4 sampler, 5 misc) */

@@ -1,18 +1,23 @@
-// Weight-streaming GEMM for the codec-LM: partial[z][j][m] = sum_{k in split z} W[m,k] * (Xhi[j,k] + Xlo[j,k])
+// Weight-streaming GEMM of the codec-LM with cluster split-K and fused epilogues.
+//
+//   out[j][m] = epilogue( sum_k W[m,k] * (Xhi[j,k] + Xlo[j,k]) + bias[m] )        j = token row, m = output feature
 //
 //   A operand = weight matrix W [Nout, Kdim] bf16 row-major (K-major), tile 128 x 64, TMA SWIZZLE_128B
 //   B operand = activations  X [2*Bpad, Kdim] bf16: rows [0,Bpad) = hi parts, rows [Bpad,2*Bpad) = lo parts
-//               (x ~= hi + lo, see split_bf16) -> one UMMA of N = 2*Bpad columns covers both, the epilogue
-//               adds column j and column j+Bpad.  The tensor pipe is idle >80% of the time in this
-//               HBM-bound regime, so the second half is free and buys ~16 mantissa bits on activations.
+//               (x ~= hi + lo, see split_bf16): one UMMA of N = 2*Bpad columns covers both; the tensor pipe is
+//               >80% idle in this HBM-bound regime, so the second half is free and buys ~16 mantissa bits.
 //   D         = fp32 accumulator in TMEM, 128 lanes (= output features) x 2*Bpad columns
 //
-// One CTA = one 128-feature tile x one K split.  Warp roles: w0 TMA producer, w1 TMEM alloc + MMA issuer
-// (single elected thread issues tcgen05.mma), w2..w5 epilogue (tcgen05.ld -> coalesced fp32 partial stores).
-// Split-K partials are reduced deterministically (fixed z order) by the consumer kernels in lm_kernels.cu.
-//
-// Replaces in the reference: F.linear at models/modules/activation.py:86 (packed QKV), :637 (out_proj),
-// models/modules/transformer.py:387 (FFN linear1/linear2) and models/voicecraft.py:181-185,1085 (logit heads).
+// Split-K without a workspace: the S CTAs of a thread-block cluster each stream one K slice of the same 128-feature
+// weight tile (so >=128 CTAs pull HBM even for a 2048 x 2048 matrix), then reduce-scatter their accumulators
+// through distributed shared memory: CTA z owns token rows [z*R, (z+1)*R), every CTA writes its partial of those
+// rows into the owner's smem (st.shared::cluster), one cluster barrier, the owner sums the S partials in fixed
+// order (deterministic) and applies the fused epilogue:
+//     EPI_QKV    q -> fp32 buffer, k/v -> appended to the paged KV cache    (activation.py:86-88, 626-631)
+//     EPI_RESID  x += y + bias                                            (transformer.py:321-329)
+//     EPI_ACT    ReLU / exact GELU -> bf16 hi/lo rows of the next GEMM      (transformer.py:387, voicecraft.py:183)
+//     EPI_LOGITS fp32 logits                                              (voicecraft.py:1085)
+// Warp roles: w0 TMA producer, w1 TMEM alloc + MMA issuer (one elected thread issues tcgen05.mma), w2..w5 epilogue.
 #include "vcb_internal.h"
 
 #include <algorithm>
@@ -28,19 +33,79 @@ struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+    static constexpr int RED_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int RED_BYTES = (BN / 2) * GEMM_BM * 4;          // [S][R][128] fp32 with S*R = Bpad
+    static constexpr int BAR_OFFSET = RED_OFFSET + RED_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16;
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_dsmem_f32(uint32_t local_smem_addr, uint32_t cta, float v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void apply_epilogue(const GemmEpilogue& ep, int row, int m, float sum) {
+    const float val = sum + ep.bias[m];
+    switch (ep.mode) {
+        case EPI_QKV: {
+            const int pos = ep.row_pos[row];
+            if (pos < 0) return;
+            const int part = m / ep.d, cc = m - part * ep.d;
+            if (part == 0) {
+                ep.qbuf[static_cast<size_t>(row) * ep.d + cc] = val;
+            } else {
+                const int slot = ep.row_slot[row];
+                const int page = ep.page_table[slot * ep.max_pages + pos / ep.page_size];
+                const int h = cc / ep.hd, e = cc - h * ep.hd;
+                const size_t off = ((static_cast<size_t>(page) * ep.H + h) * ep.page_size + pos % ep.page_size) * ep.hd + e;
+                void* pool = (part == 1) ? ep.kpool : ep.vpool;
+                if (ep.kv_fp32) static_cast<float*>(pool)[off] = val;
+                else static_cast<__nv_bfloat16*>(pool)[off] = __float2bfloat16_rn(val);
+            }
+            break;
+        }
+        case EPI_RESID: {
+            float* p = ep.x + static_cast<size_t>(row) * ep.ld_out + m;
+            *p = *p + val;
+            break;
+        }
+        case EPI_ACT: {
+            float u = val;
+            if (ep.act_kind == 1) u = fmaxf(u, 0.f);
+            else if (ep.act_kind == 2) u = 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f));
+            __nv_bfloat16 hi, lo;
+            split_bf16(u, hi, lo);
+            ep.act[static_cast<size_t>(row) * ep.ld_out + m] = hi;
+            ep.act[static_cast<size_t>(row + ep.bpad_out) * ep.ld_out + m] = lo;
+            break;
+        }
+        default:
+            ep.out[static_cast<size_t>(row) * ep.ld_out + ep.col_off + m] = val;
+    }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
-gemm_w_xT_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ partial, int Nout, int ldp, int total_kb, int kb_per_split,
-                 int b_col_off, int nvalid) {
+gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmEpilogue ep, int Nout, int total_kb, int kb_per_split, int b_col_off, int nvalid) {
     using L = GemmSmem<BN, STAGES>;
     constexpr int BPAD = BN / 2;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];       // SWIZZLE_128B tiles need 1024-byte alignment
+    float* red = reinterpret_cast<float*>(smem + L::RED_OFFSET);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
@@ -48,11 +113,15 @@ gemm_w_xT_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * GEMM_BM;
-    const int z = blockIdx.z;
+    const int S = static_cast<int>(cluster_nctarank());      // K splits = cluster size
+    const int z = static_cast<int>(cluster_ctarank());
+    const int m0 = (blockIdx.x / S) * GEMM_BM;
     const int kb0 = z * kb_per_split;
-    const int nkb = min(kb_per_split, total_kb - kb0);
+    const int nkb = max(0, min(kb_per_split, total_kb - kb0));
+    const int pre = min(nkb, STAGES);
 
+    pdl_launch_dependents();        // dependents may be scheduled now; their griddepcontrol.wait still orders the data
+    if (threadIdx.x == 0) tl_mark(0x100 + ep.mode);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -62,34 +131,33 @@ gemm_w_xT_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         mbar_init(tmem_full, 1);
         mbar_fence_init();
+        // Weights never depend on the previous kernel: their first STAGES tiles go in flight right away
+        // (under PDL: while the producer grid is still draining); activations wait for griddepcontrol.wait.
+        for (int i = 0; i < pre; ++i) {
+            mbar_arrive_expect_tx(&full_bar[i], L::STAGE_BYTES);
+            tma_load_2d(smem + i * L::STAGE_BYTES, &tmA, &full_bar[i], (kb0 + i) * GEMM_BK, m0);
+        }
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();             // CTA-wide sync + "every CTA of the cluster has started" (required before DSMEM)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer ==========================================================================
         if (lane == 0) {
-            // Weights never depend on the previous kernel: under PDL their first STAGES tiles are in
-            // flight before the producer grid has drained; activations wait for griddepcontrol.wait.
-            const int pre = min(nkb, STAGES);
-            for (int i = 0; i < pre; ++i) {
-                mbar_arrive_expect_tx(&full_bar[i], L::STAGE_BYTES);
-                tma_load_2d(smem + i * L::STAGE_BYTES, &tmA, &full_bar[i], (kb0 + i) * GEMM_BK, m0);
-            }
             pdl_wait();
+            tl_mark(0x110 + ep.mode);
             for (int i = 0; i < pre; ++i)
                 tma_load_2d(smem + i * L::STAGE_BYTES + L::A_BYTES, &tmB, &full_bar[i],
                             b_col_off + (kb0 + i) * GEMM_BK, 0);
             int stage = 0, phase = 0;                       // state after the first `pre` fills
             for (int i = pre; i < nkb; ++i) {
-                // stage `stage` was filled in the previous round; wait until the MMA released it
-                mbar_wait(&empty_bar[stage], phase);
+                mbar_wait(&empty_bar[stage], phase);        // the MMA released this slot
                 mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                 uint8_t* a = smem + stage * L::STAGE_BYTES;
                 tma_load_2d(a, &tmA, &full_bar[stage], (kb0 + i) * GEMM_BK, m0);
@@ -109,68 +177,96 @@ gemm_w_xT_splitk(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
                 const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + L::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) {
-                    // advance 16 K-elements = 32 bytes inside the 128B swizzle row: +2 in the (>>4) address field
+                for (int k = 0; k < GEMM_BK / 16; ++k)     // +32 B per 16 K-elements inside the swizzle row
                     umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
-                }
-                umma_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
-                if (i == nkb - 1) umma_commit(tmem_full);       // accumulator complete
+                umma_commit(&empty_bar[stage]);             // frees the smem slot when the MMAs retire
+                if (i == nkb - 1) umma_commit(tmem_full);   // accumulator complete
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> fp32 partials =========================================
-        pdl_launch_dependents();
-        const int q = warp & 3;                                 // TMEM lane quarter owned by this warp
-        const int m = m0 + q * 32 + lane;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
+        // ===== epilogue part 1: TMEM -> registers -> reduce-scatter over the cluster (DSMEM) =========
+        const int q = warp & 3;                             // TMEM lane quarter owned by this warp
+        const int ml = q * 32 + lane;                       // feature inside the tile
+        const int R = BPAD / S;                             // token rows owned by each CTA of the cluster
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        if (threadIdx.x == 64) tl_mark(0x120 + ep.mode);
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        float* out = partial + (static_cast<size_t>(z) * BPAD) * ldp + m;
+        const uint32_t red_addr = smem_u32(red);
         constexpr int CH = BPAD < 32 ? 16 : 32;
 #pragma unroll 1
         for (int c = 0; c < BPAD; c += CH) {
             float hi[CH], lo[CH];
-            if constexpr (CH == 32) {
-                tmem_ld_32x32(lane_addr + c, hi);
-                tmem_ld_32x32(lane_addr + BPAD + c, lo);
+            if (nkb > 0) {
+                if constexpr (CH == 32) {
+                    tmem_ld_32x32(lane_addr + c, hi);
+                    tmem_ld_32x32(lane_addr + BPAD + c, lo);
+                } else {
+                    tmem_ld_32x16(lane_addr + c, hi);
+                    tmem_ld_32x16(lane_addr + BPAD + c, lo);
+                }
             } else {
-                tmem_ld_32x16(lane_addr + c, hi);
-                tmem_ld_32x16(lane_addr + BPAD + c, lo);
-            }
-            if (m < Nout) {
 #pragma unroll
-                for (int j = 0; j < CH; ++j)
-                    if (c + j < nvalid) out[static_cast<size_t>(c + j) * ldp] = hi[j] + lo[j];
+                for (int j = 0; j < CH; ++j) hi[j] = lo[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int row = c + j;
+                if (row < nvalid) {
+                    const int owner = row / R, rr = row - owner * R;
+                    st_dsmem_f32(red_addr + static_cast<uint32_t>(((z * R + rr) * GEMM_BM + ml) * 4), owner, hi[j] + lo[j]);
+                }
             }
         }
         tc_fence_before();
     }
+    cluster_sync_all();                                     // all partials have landed in their owners' smem
+    if (warp >= 2) {
+        // ===== epilogue part 2: fixed-order sum of the S partials of my R rows + fused epilogue =======
+        const int q = warp & 3;
+        const int ml = q * 32 + lane;
+        const int m = m0 + ml;
+        const int R = BPAD / S;
+        if (m < Nout) {
+            for (int rr = 0; rr < R; ++rr) {
+                const int row = z * R + rr;
+                if (row >= nvalid) break;
+                float s = 0.f;
+                for (int zz = 0; zz < S; ++zz) s += red[(zz * R + rr) * GEMM_BM + ml];
+                apply_epilogue(ep, row, m, s);
+            }
+        }
+    }
     __syncthreads();
+    if (threadIdx.x == 0) tl_mark(0x130 + ep.mode);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
     }
 }
 
+void gemm_timeline_set(unsigned long long* buf, unsigned int* cnt) {
+    cudaMemcpyToSymbol(g_tl_buf, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(g_tl_cnt, &cnt, sizeof(cnt));
+}
+
 // ---------------------------------------------------------------------------------------------------
-// Bring-up / cross-check kernel: same contract on CUDA cores (one warp per output feature).  Selected
-// with VCB_GEMM_IMPL=simt; never the default.  It exists so a tcgen05 descriptor bug can be told apart
-// from a bug anywhere else in the step.
+// Bring-up / cross-check kernel: same contract on CUDA cores (one warp per output feature, no split).
+// Selected with VCB_GEMM_IMPL=simt; never the default.  It exists so a tcgen05 descriptor bug can be told
+// apart from a bug anywhere else in the step.
 // ---------------------------------------------------------------------------------------------------
 __global__ void gemm_w_xT_simt(const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ X,
-                               float* __restrict__ partial, int Nout, int Kdim, int ldx, int ldp, int bpad,
-                               int total_kb, int kb_per_split, int b_col_off, int nvalid) {
+                               const GemmEpilogue ep, int Nout, int Kdim, int ldx, int bpad, int b_col_off, int nvalid) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int z = blockIdx.z;
     if (warp >= Nout) return;
-    const int k0 = z * kb_per_split * GEMM_BK;
-    const int k1 = min(Kdim, (z * kb_per_split + min(kb_per_split, total_kb - z * kb_per_split)) * GEMM_BK);
     for (int j = 0; j < nvalid; ++j) {
         float acc = 0.f;
-        for (int k = k0 + lane; k < k1; k += 32) {
+        for (int k = lane; k < Kdim; k += 32) {
             const float w = __bfloat162float(W[static_cast<size_t>(warp) * Kdim + k]);
             const float xh = __bfloat162float(X[static_cast<size_t>(j) * ldx + b_col_off + k]);
             const float xl = __bfloat162float(X[static_cast<size_t>(j + bpad) * ldx + b_col_off + k]);
@@ -178,7 +274,7 @@ __global__ void gemm_w_xT_simt(const __nv_bfloat16* __restrict__ W, const __nv_b
             acc = fmaf(w, xl, acc);
         }
         acc = warp_sum(acc);
-        if (lane == 0) partial[(static_cast<size_t>(z) * bpad + j) * ldp + warp] = acc;
+        if (lane == 0) apply_epilogue(ep, j, warp, acc);
     }
 }
 
@@ -230,24 +326,29 @@ static int launch_one(const GemmCall& g, cudaStream_t st) {
     using L = GemmSmem<BN, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        VCB_CUDA_OK(cudaFuncSetAttribute(gemm_w_xT_splitk<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VCB_CUDA_OK(cudaFuncSetAttribute(gemm_w_xT_cluster<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL));
         attr_set = true;
     }
+    const int tiles = (g.Nout + GEMM_BM - 1) / GEMM_BM;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((g.Nout + GEMM_BM - 1) / GEMM_BM, 1, g.splits);
+    cfg.gridDim = dim3(tiles * g.splits, 1, 1);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = g.pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = g.splits;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g.pdl ? 2 : 1;
     const int total_kb = g.Kdim / GEMM_BK;
     const int kbps = (total_kb + g.splits - 1) / g.splits;
-    VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_w_xT_splitk<BN, STAGES>, *g.tmA, *g.tmB, g.partial, g.Nout, g.ldp,
-                                   total_kb, kbps, g.b_col_off, g.nvalid));
+    VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_w_xT_cluster<BN, STAGES>, *g.tmA, *g.tmB, g.ep, g.Nout, total_kb, kbps,
+                                   g.b_col_off, g.nvalid));
     return 0;
 }
 
@@ -256,36 +357,42 @@ int gemm_launch(const GemmCall& g, cudaStream_t st) {
         set_error("gemm: K=%d not a multiple of %d", g.Kdim, GEMM_BK);
         return -1;
     }
-    const int total_kb = g.Kdim / GEMM_BK;
-    const int kbps = (total_kb + g.splits - 1) / g.splits;
-    if ((g.splits - 1) * kbps >= total_kb) {
-        set_error("gemm: splits=%d leaves an empty split for %d k-blocks", g.splits, total_kb);
-        return -1;
-    }
     if (g.simt) {
-        dim3 grid((g.Nout * 32 + 255) / 256, 1, g.splits);
-        gemm_w_xT_simt<<<grid, 256, 0, st>>>(g.W, g.X, g.partial, g.Nout, g.Kdim, g.ldx, g.ldp, g.bpad, total_kb,
-                                             kbps, g.b_col_off, g.nvalid);
+        dim3 grid((g.Nout * 32 + 255) / 256, 1, 1);
+        gemm_w_xT_simt<<<grid, 256, 0, st>>>(g.W, g.X, g.ep, g.Nout, g.Kdim, g.ldx, g.bpad, g.b_col_off, g.nvalid);
         VCB_CUDA_OK(cudaGetLastError());
         return 0;
     }
+    const int total_kb = g.Kdim / GEMM_BK;
+    const int kbps = (total_kb + g.splits - 1) / g.splits;
+    if (g.splits < 1 || g.splits > 8 || (g.splits & (g.splits - 1)) || g.bpad % g.splits ||
+        (g.splits - 1) * kbps >= total_kb) {
+        set_error("gemm: bad split count %d for %d k-blocks, bpad %d", g.splits, total_kb, g.bpad);
+        return -1;
+    }
     switch (g.bpad) {
         case 16: return launch_one<32, 4>(g, st);
-        case 32: return launch_one<64, 4>(g, st);     // 4 x 24 KB: two CTAs per SM stay resident (PDL overlap)
+        case 32:
+            if (g.stages == 2) return launch_one<64, 2>(g, st);
+            if (g.stages == 3) return launch_one<64, 3>(g, st);
+            if (g.stages == 6) return launch_one<64, 6>(g, st);
+            if (g.stages == 8) return launch_one<64, 8>(g, st);
+            return launch_one<64, 4>(g, st);     // 4 x 24 KB + 16 KB: two CTAs per SM stay resident (PDL overlap)
         case 64: return launch_one<128, 3>(g, st);
-        case 128: return launch_one<256, 4>(g, st);
+        case 128: return launch_one<256, 3>(g, st);
         default: set_error("gemm: unsupported bpad %d", g.bpad); return -1;
     }
 }
 
+// Cluster size (= K splits), a power of two <= 8.  Measured on B200 (scripts/bench_gemm.py, profiles/r01_gemm_micro.txt):
+// the kernel has a ~7 us latency floor, so the grid should reach >= ~1.3 CTAs per SM in ONE wave of co-resident CTAs
+// (2 per SM) while every split keeps >= 4 k-blocks.
 int gemm_pick_splits(int Nout, int Kdim, int num_sms) {
-    // ~1.5 CTAs per SM so every SM streams weights, but at least 4 k-blocks (32 KB of weights) per CTA
     const int tiles = (Nout + GEMM_BM - 1) / GEMM_BM;
     const int total_kb = Kdim / GEMM_BK;
-    int s = (3 * num_sms / 2 + tiles - 1) / tiles;
-    s = std::min(s, std::max(1, total_kb / 4));
-    s = std::max(1, std::min(s, 16));
-    while (s > 1 && (s - 1) * ((total_kb + s - 1) / s) >= total_kb) --s;
+    int s = 1;
+    while (s < 8 && tiles * s < num_sms && total_kb / (2 * s) >= 4) s *= 2;
+    while (s > 1 && (s - 1) * ((total_kb + s - 1) / s) >= total_kb) s /= 2;
     return s;
 }
 

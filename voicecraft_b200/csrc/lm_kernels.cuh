@@ -68,18 +68,19 @@ __global__ void embed_rows_kernel(const EmbedSeq* __restrict__ seqs, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Row reduce + LayerNorm:  x' = x[src] + bias + sum_z partial[z][row]   (residual + split-K reduce, fixed z order)
-//                          y  = LN(x') * gamma + beta  ->  bf16 hi / lo rows of the next GEMM's B operand
-// Replaces F.layer_norm (transformer.py:62-75) and the residual adds (:321-329).
+// LayerNorm of the fp32 residual stream -> bf16 hi / lo rows of the next GEMM's B operand.
+// Replaces F.layer_norm (transformer.py:62-75); the residual adds live in the GEMM epilogue (EPI_RESID).
+// One CTA per row; two-pass variance in registers.
 // ---------------------------------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-ln_rows_kernel(const float* __restrict__ x_in, const int* __restrict__ src_index, float* __restrict__ x_out,
-               const float* __restrict__ partial, int nsplit, int ldp, int bpad, const float* __restrict__ bias,
-               const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ act,
-               int ld_act, int d, float eps) {
+ln_rows_kernel(const float* __restrict__ x_in, const int* __restrict__ src_index, const float* __restrict__ gamma,
+               const float* __restrict__ beta, __nv_bfloat16* __restrict__ act, int ld_act, int bpad, int d, float eps) {
     __shared__ float red[8];
+    pdl_launch_dependents();          // let the consumer GEMM start prefetching its weights right away
+    if (threadIdx.x == 0) tl_mark(0x200);
     pdl_wait();
+    if (threadIdx.x == 0) tl_mark(0x210);
     const int r = blockIdx.x;
     const int src = src_index ? src_index[r] : r;
     float v[MAXV];
@@ -87,18 +88,8 @@ ln_rows_kernel(const float* __restrict__ x_in, const int* __restrict__ src_index
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
         const int c = threadIdx.x + j * 256;
-        float t = 0.f;
-        if (c < d) {
-            t = x_in[static_cast<size_t>(src) * d + c];
-            if (nsplit > 0) {
-                float u = bias[c];
-                for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
-                t += u;
-            }
-            if (x_out) x_out[static_cast<size_t>(r) * d + c] = t;
-        }
-        v[j] = t;
-        s += t;
+        v[j] = (c < d) ? x_in[static_cast<size_t>(src) * d + c] : 0.f;
+        s += v[j];
     }
     const float mean = block_sum_256(s, red) / d;
     float q = 0.f;
@@ -112,7 +103,6 @@ ln_rows_kernel(const float* __restrict__ x_in, const int* __restrict__ src_index
     }
     const float var = block_sum_256(q, red) / d;
     const float rstd = 1.0f / sqrtf(var + eps);
-    pdl_launch_dependents();
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
         const int c = threadIdx.x + j * 256;
@@ -124,74 +114,31 @@ ln_rows_kernel(const float* __restrict__ x_in, const int* __restrict__ src_index
             act[static_cast<size_t>(r + bpad) * ld_act + c] = lo;
         }
     }
+    if (threadIdx.x == 0) tl_mark(0x230);
 }
 
-// x' = x + bias + sum_z partial  ->  out[out_index[row]]   (hidden state of the last token of each utterance)
-__global__ void reduce_rows_kernel(const float* __restrict__ x_in, const float* __restrict__ partial, int nsplit,
-                                   int ldp, int bpad, const float* __restrict__ bias, float* __restrict__ out,
+// hidden state of the last token of each utterance: out[out_index[row]] = x[row]   (prefill -> first sampling step)
+__global__ void gather_rows_kernel(const float* __restrict__ x_in, float* __restrict__ out,
                                    const int* __restrict__ out_index, int d) {
+    pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x;
     const int dst = out_index[r];
     if (dst < 0) return;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-        float u = bias[c];
-        for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
-        out[static_cast<size_t>(dst) * d + c] = x_in[static_cast<size_t>(r) * d + c] + u;
-    }
+    for (int c = threadIdx.x; c < d; c += blockDim.x)
+        out[static_cast<size_t>(dst) * d + c] = x_in[static_cast<size_t>(r) * d + c];
 }
 
-// act = f(sum_z partial + bias) -> bf16 hi/lo.  f: 1 = ReLU (transformer.py:387), 2 = exact GELU (voicecraft.py:183)
-__global__ void bias_act_kernel(const float* __restrict__ partial, int nsplit, int ldp, int bpad,
-                                const float* __restrict__ bias, int N, int act_kind,
-                                __nv_bfloat16* __restrict__ act, int ld_act) {
-    pdl_wait();
+// fp32 rows -> bf16 hi/lo rows (bring-up hook vcb_debug_gemm only)
+__global__ void split_rows_kernel(const float* __restrict__ x, int N, __nv_bfloat16* __restrict__ act, int ld_act,
+                                  int bpad) {
     const int r = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
-    float u = bias[c];
-    for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
-    if (act_kind == 1) u = fmaxf(u, 0.f);
-    else if (act_kind == 2) u = 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f));
     __nv_bfloat16 hi, lo;
-    split_bf16(u, hi, lo);
+    split_bf16(x[static_cast<size_t>(r) * N + c], hi, lo);
     act[static_cast<size_t>(r) * ld_act + c] = hi;
     act[static_cast<size_t>(r + bpad) * ld_act + c] = lo;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// QKV finish: q -> fp32 [rows, d]; k, v -> appended in place to the paged KV cache at (slot, pos).
-// Replaces the unflatten/transpose copy (activation.py:88) and BOTH cache re-allocations
-// (activation.py:627-631 torch.cat per layer, voicecraft.py:1081 torch.cat of the whole cache).
-// KV pool layout per layer: [page][head][KV_PAGE tokens][hd]  -> one (page, head) slab is contiguous.
-// ---------------------------------------------------------------------------------------------------
-template <typename KVT>
-__global__ void qkv_finish_kernel(const float* __restrict__ partial, int nsplit, int ldp, int bpad,
-                                  const float* __restrict__ bias, float* __restrict__ qbuf, KVT* __restrict__ kpool,
-                                  KVT* __restrict__ vpool, const int* __restrict__ page_table, int max_pages,
-                                  const int* __restrict__ row_slot, const int* __restrict__ row_pos, int d, int H,
-                                  int hd) {
-    pdl_wait();
-    const int r = blockIdx.x;
-    const int pos = row_pos[r];
-    if (pos < 0) return;
-    const int slot = row_slot[r];
-    const int page = page_table[slot * max_pages + pos / KV_PAGE];
-    const int tok = pos % KV_PAGE;
-    for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
-        float u = bias[c];
-        for (int z = 0; z < nsplit; ++z) u += partial[(static_cast<size_t>(z) * bpad + r) * ldp + c];
-        const int part = c / d, cc = c - part * d;
-        if (part == 0) {
-            qbuf[static_cast<size_t>(r) * d + cc] = u;
-        } else {
-            const int h = cc / hd, e = cc - h * hd;
-            const size_t off = ((static_cast<size_t>(page) * H + h) * KV_PAGE + tok) * hd + e;
-            KVT* pool = (part == 1) ? kpool : vpool;
-            if constexpr (sizeof(KVT) == 2) pool[off] = __float2bfloat16_rn(u);
-            else pool[off] = u;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -252,7 +199,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, const KVT* __restrict__ vpool,
                  const int* __restrict__ page_table, int max_pages, const int* __restrict__ row_slot,
                  const int* __restrict__ row_pos, int H, __nv_bfloat16* __restrict__ act, int ld_act, int bpad,
-                 float scale) {
+                 float scale, float* __restrict__ ws, int* __restrict__ cnt, int maxch, int chunk_pages) {
     using L = AttSmem<KVT, HD>;
     constexpr int LPT = HD / 8;          // lanes per key in QK
     constexpr int TPW = 32 / LPT;        // keys per warp iteration
@@ -264,30 +211,40 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
     float* pw = reinterpret_cast<float*>(att_smem + L::OFF_PW);
     float* red = reinterpret_cast<float*>(att_smem + L::OFF_RED);
     uint64_t* bar = reinterpret_cast<uint64_t*>(att_smem + L::OFF_BAR);
+    __shared__ int s_last;
 
-    const int r = blockIdx.x / H, h = blockIdx.x % H;
+    const int rh = blockIdx.x;
+    const int r = rh / H, h = rh % H;
+    const int chunk = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         for (int s = 0; s < ATT_STAGES; ++s) mbar_init(&bar[s], 1);
         mbar_fence_init();
     }
+    if (threadIdx.x == 0) tl_mark(0x300);
     pdl_wait();
+    if (threadIdx.x == 0) tl_mark(0x310);
     const int pos = row_pos[r];
     if (pos < 0) return;
-    const int slot = row_slot[r];
     const int npages = pos / KV_PAGE + 1;
+    const int nch = (npages + chunk_pages - 1) / chunk_pages;      // flash-decoding style split over the context
+    if (chunk >= nch) return;
+    const int p0 = chunk * chunk_pages;
+    const int p1 = min(npages, p0 + chunk_pages);
+    const int slot = row_slot[r];
     const int* pt = page_table + slot * max_pages;
     __syncthreads();
 
     auto issue = [&](int p) {
-        const int s = p % ATT_STAGES;
+        const int s = (p - p0) % ATT_STAGES;
         const size_t off = (static_cast<size_t>(pt[p]) * H + h) * KV_PAGE * HD;
         mbar_arrive_expect_tx(&bar[s], 2 * L::PAGE_BYTES);
         tma_bulk_g2s(sK + s * KV_PAGE * HD, kpool + off, L::PAGE_BYTES, &bar[s]);
         tma_bulk_g2s(sV + s * KV_PAGE * HD, vpool + off, L::PAGE_BYTES, &bar[s]);
     };
     if (threadIdx.x == 0)
-        for (int p = 0; p < min(npages, ATT_STAGES); ++p) issue(p);
+        for (int p = p0; p < min(p1, p0 + ATT_STAGES); ++p) issue(p);
 
     const int sub = lane % LPT;
     float q[8];
@@ -301,9 +258,9 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
 #pragma unroll
     for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
 
-    for (int p = 0; p < npages; ++p) {
-        const int s = p % ATT_STAGES;
-        mbar_wait(&bar[s], (p / ATT_STAGES) & 1);
+    for (int p = p0; p < p1; ++p) {
+        const int s = (p - p0) % ATT_STAGES;
+        mbar_wait(&bar[s], ((p - p0) / ATT_STAGES) & 1);
         const KVT* K = sK + s * KV_PAGE * HD;
         const KVT* V = sV + s * KV_PAGE * HD;
         // ---- scores for this warp's 16 keys
@@ -324,11 +281,11 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
         const float s0 = sc[lane], s1 = sc[lane + 32];
         const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
         const float corr = expf(m_run - m_new);
-        const float p0 = expf(s0 - m_new), p1 = expf(s1 - m_new);
+        const float p0_ = expf(s0 - m_new), p1_ = expf(s1 - m_new);
         float* mypw = pw + warp * KV_PAGE;
-        mypw[lane] = p0;
-        mypw[lane + 32] = p1;
-        l_run = l_run * corr + warp_sum(p0 + p1);
+        mypw[lane] = p0_;
+        mypw[lane + 32] = p1_;
+        l_run = l_run * corr + warp_sum(p0_ + p1_);
         m_run = m_new;
         __syncwarp();
         // ---- PV for this warp's 16 keys
@@ -344,21 +301,55 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
             for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
         }
         __syncthreads();                                   // everyone is done with stage s
-        if (threadIdx.x == 0 && p + ATT_STAGES < npages) issue(p + ATT_STAGES);
+        if (threadIdx.x == 0 && p + ATT_STAGES < p1) issue(p + ATT_STAGES);
     }
-    pdl_launch_dependents();
+    if (threadIdx.x == 0) tl_mark(0x330);
     // ---- combine the 4 warps' partial outputs
 #pragma unroll
     for (int i = 0; i < DPT; ++i) red[warp * HD + lane * DPT + i] = acc[i];
     __syncthreads();
+    const size_t ocol = static_cast<size_t>(h) * HD;
+    if (nch == 1) {
+        for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
+            const float o = (red[dd] + red[HD + dd] + red[2 * HD + dd] + red[3 * HD + dd]) / l_run;
+            __nv_bfloat16 hi, lo;
+            split_bf16(o, hi, lo);
+            act[static_cast<size_t>(r) * ld_act + ocol + dd] = hi;
+            act[static_cast<size_t>(r + bpad) * ld_act + ocol + dd] = lo;
+        }
+        return;
+    }
+    // ---- split context: publish (o, m, l); the last chunk to finish merges all chunks in chunk order
+    float* myws = ws + (static_cast<size_t>(rh) * maxch + chunk) * (HD + 2);
+    for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS)
+        myws[dd] = red[dd] + red[HD + dd] + red[2 * HD + dd] + red[3 * HD + dd];
+    if (threadIdx.x == 0) {
+        myws[HD] = m_run;
+        myws[HD + 1] = l_run;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&cnt[rh], 1) == nch - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile float* base = ws + static_cast<size_t>(rh) * maxch * (HD + 2);
+    float M = -INFINITY;
+    for (int c = 0; c < nch; ++c) M = fmaxf(M, base[c * (HD + 2) + HD]);
     for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
-        const float o = (red[dd] + red[HD + dd] + red[2 * HD + dd] + red[3 * HD + dd]) / l_run;
+        float Lsum = 0.f, O = 0.f;
+        for (int c = 0; c < nch; ++c) {
+            const float w = expf(base[c * (HD + 2) + HD] - M);
+            Lsum += base[c * (HD + 2) + HD + 1] * w;
+            O += base[c * (HD + 2) + dd] * w;
+        }
+        const float o = O / Lsum;
         __nv_bfloat16 hi, lo;
         split_bf16(o, hi, lo);
-        const size_t c = static_cast<size_t>(h) * HD + dd;
-        act[static_cast<size_t>(r) * ld_act + c] = hi;
-        act[static_cast<size_t>(r + bpad) * ld_act + c] = lo;
+        act[static_cast<size_t>(r) * ld_act + ocol + dd] = hi;
+        act[static_cast<size_t>(r + bpad) * ld_act + ocol + dd] = lo;
     }
+    if (threadIdx.x == 0) cnt[rh] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -369,6 +360,8 @@ __global__ void step_prep_kernel(const int* __restrict__ slots, int n, SlotState
                                  const GroupState* __restrict__ gr, int* __restrict__ row_slot,
                                  int* __restrict__ row_pos, int* __restrict__ row_last,
                                  const float* __restrict__ x_slot, float* __restrict__ x_rows, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x;
     const int slot = slots[r];
     __shared__ int s_pos;
@@ -412,9 +405,8 @@ struct SamplerArgs {
     int n;
     SlotState* st;
     GroupState* gr;
-    const float* partial;     // logits partials [nsplit][bpad][ldp], column = k*Vpad + v
-    int nsplit, ldp, bpad;
-    const float* const* bias2;   // [K] -> [V]
+    const float* logits;      // [n][ldl] fp32 (bias included), column = k*Vpad + v
+    int ldl;
     const float* noise;       // [n*K][V]
     float* dbg_logits;        // [n*K][V] or null
     int* tok_log;             // [max_slots][max_steps][K]
@@ -444,7 +436,10 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
     __shared__ int s_flag;
     extern __shared__ unsigned long long sort_buf[];     // SAMP_SORT_N entries (only used when top_p < 1)
 
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) tl_mark(0x400);
     pdl_wait();
+    if (threadIdx.x == 0) tl_mark(0x410);
     const int i = blockIdx.x / a.K, k = blockIdx.x % a.K;
     const int slot = a.slots[i];
     SlotState& S = a.st[slot];
@@ -495,9 +490,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
         const int v = tid + j * SAMP_THREADS;
         float u = -INFINITY;
         if (v < V) {
-            u = a.bias2[k][v];
-            for (int z = 0; z < a.nsplit; ++z)
-                u += a.partial[(static_cast<size_t>(z) * a.bpad + i) * a.ldp + k * a.Vpad + v];
+            u = a.logits[static_cast<size_t>(i) * a.ldl + k * a.Vpad + v];
             if (a.dbg_logits) a.dbg_logits[static_cast<size_t>(row) * V + v] = u;
             if (a.eos > 0 && v == (tts ? a.eog : a.eos)) u = -10000.f;                   // :1091-1093 / :816-818
             if (n_eog == 0) {

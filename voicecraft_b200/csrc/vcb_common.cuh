@@ -102,6 +102,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
         : "memory");
 }
 
+// Optional device-side timeline (debug): CTA 0 of instrumented kernels appends (tag, globaltimer ns) records.
+// Each translation unit has its own copy of the pointer; the host sets them through vcb_timeline_set().
+static __device__ unsigned long long* g_tl_buf = nullptr;
+static __device__ unsigned int* g_tl_cnt = nullptr;
+__device__ __forceinline__ void tl_mark(unsigned int tag) {
+    if (g_tl_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned int i = atomicAdd(g_tl_cnt, 1u);
+        if (i < 65536u) {
+            g_tl_buf[2 * i] = tag;
+            g_tl_buf[2 * i + 1] = t;
+        }
+    }
+}
+
 // Programmatic dependent launch (PDL): wait for the producer grid / let the consumer grid start.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

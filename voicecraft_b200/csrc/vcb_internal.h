@@ -11,17 +11,39 @@ namespace vcb {
 // ---------------------------------------------------------------------------------------------------
 // GEMM (gemm_tcgen05.cu)
 // ---------------------------------------------------------------------------------------------------
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_ACT = 2, EPI_LOGITS = 3 };
+
+// Fused epilogue of the GEMM (applied by the CTA that owns the row after the cluster reduce-scatter).
+struct GemmEpilogue {
+    int mode = EPI_LOGITS;
+    const float* bias = nullptr;          // [Nout]
+    // EPI_QKV: q -> qbuf [rows, d]; k, v -> paged KV cache at (row_slot, row_pos)
+    float* qbuf = nullptr;
+    void* kpool = nullptr;
+    void* vpool = nullptr;
+    const int* page_table = nullptr;
+    const int* row_slot = nullptr;
+    const int* row_pos = nullptr;
+    int kv_fp32 = 0, max_pages = 0, page_size = 64, d = 0, H = 0, hd = 0;
+    // EPI_RESID: x[row, m] += y ; EPI_ACT: act hi/lo rows ; EPI_LOGITS: out[row, col_off + m]
+    float* x = nullptr;
+    __nv_bfloat16* act = nullptr;
+    float* out = nullptr;
+    int ld_out = 0, col_off = 0, act_kind = 0, bpad_out = 0;
+};
+
 struct GemmCall {
     const CUtensorMap* tmA = nullptr;   // weights [Nout, Kdim]
     const CUtensorMap* tmB = nullptr;   // activations [2*bpad, ldx]
     const __nv_bfloat16* W = nullptr;   // raw pointers (simt cross-check path only)
     const __nv_bfloat16* X = nullptr;
-    float* partial = nullptr;           // [splits][bpad][ldp]
-    int Nout = 0, Kdim = 0, ldx = 0, ldp = 0, bpad = 0, splits = 1, b_col_off = 0, nvalid = 0;
-    int pdl = 0, simt = 0;
+    GemmEpilogue ep;
+    int Nout = 0, Kdim = 0, ldx = 0, bpad = 0, splits = 1, b_col_off = 0, nvalid = 0;
+    int pdl = 0, simt = 0, stages = 0;
 };
 int gemm_launch(const GemmCall& g, cudaStream_t st);
 int gemm_pick_splits(int Nout, int Kdim, int num_sms);
+void gemm_timeline_set(unsigned long long* buf, unsigned int* cnt);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows);
 
