@@ -20,10 +20,10 @@ buf = (C.c_uint64 * (2 * 65536))(); n = C.c_int32()
 lib.vcb_timeline(0, buf, 65536, C.byref(n))
 recs = sorted(((buf[2*i+1], buf[2*i]) for i in range(n.value)))
 t0 = recs[0][0]
-names = {0x100:"gemm.start",0x110:"gemm.waited",0x120:"gemm.acc_ready",0x130:"gemm.end",0x200:"ln.start",0x210:"ln.waited",0x230:"ln.end",
+names = {0x100:"gemm.start",0x110:"gemm.waited",0x120:"gemm.acc_ready",0x130:"gemm.end",0x140:"gemm.dsmem_sent",0x150:"gemm.cluster_synced",0x160:"gemm.epi_done",0x200:"ln.start",0x210:"ln.waited",0x230:"ln.end",
          0x300:"attn.start",0x310:"attn.waited",0x330:"attn.end",0x400:"samp.start",0x410:"samp.waited"}
 modes = ["qkv","resid","act","logits"]
-for t, tag in recs[: 2 * 140 * 3 // 2]:
+for t, tag in recs[: 120]:
     base = tag & ~0xf if (tag & 0xf00) == 0x100 else tag
     nm = names.get(base, hex(tag))
     if (tag & 0xf00) == 0x100: nm += "." + modes[tag & 0xf]

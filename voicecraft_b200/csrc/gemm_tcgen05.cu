@@ -2,7 +2,10 @@
 //
 //   out[j][m] = epilogue( sum_k W[m,k] * (Xhi[j,k] + Xlo[j,k]) + bias[m] )        j = token row, m = output feature
 //
-//   A operand = weight matrix W [Nout, Kdim] bf16 row-major (K-major), tile 128 x 64, TMA SWIZZLE_128B
+//   A operand = weight matrix W [Nout, Kdim] bf16, PRE-TILED in HBM: tile (mt, kb) = W[mt*128.., kb*64..] is one
+//               contiguous 16 KB block [128 rows][64 cols] at block index mt*KB + kb (pack_weight_tiles), so every
+//               TMA box is a single sequential DRAM burst (a row-major matrix would scatter a box over 128 DRAM
+//               pages -- measured 18% DRAM utilisation in ncu).  TMA SWIZZLE_128B into smem.
 //   B operand = activations  X [2*Bpad, Kdim] bf16: rows [0,Bpad) = hi parts, rows [Bpad,2*Bpad) = lo parts
 //               (x ~= hi + lo, see split_bf16): one UMMA of N = 2*Bpad columns covers both; the tensor pipe is
 //               >80% idle in this HBM-bound regime, so the second half is free and buys ~16 mantissa bits.
@@ -58,50 +61,75 @@ __device__ __forceinline__ void st_dsmem_f32(uint32_t local_smem_addr, uint32_t 
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 
-__device__ __forceinline__ void apply_epilogue(const GemmEpilogue& ep, int row, int m, float sum) {
-    const float val = sum + ep.bias[m];
+// Fused epilogue for up to 4 token rows of one output feature m.  All loads of the group are issued before the first
+// dependent use (the per-row chains position -> page -> address would otherwise serialise on L2 latency).
+__device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0, int nrows, int m, const float (&sum)[4],
+                                                float bias) {
     switch (ep.mode) {
         case EPI_QKV: {
-            const int pos = ep.row_pos[row];
-            if (pos < 0) return;
+            int pos[4], slot[4], page[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pos[u] = (u < nrows) ? ep.row_pos[row0 + u] : -1;
+                slot[u] = (u < nrows) ? ep.row_slot[row0 + u] : 0;
+            }
             const int part = m / ep.d, cc = m - part * ep.d;
             if (part == 0) {
-                ep.qbuf[static_cast<size_t>(row) * ep.d + cc] = val;
-            } else {
-                const int slot = ep.row_slot[row];
-                const int page = ep.page_table[slot * ep.max_pages + pos / ep.page_size];
-                const int h = cc / ep.hd, e = cc - h * ep.hd;
-                const size_t off = ((static_cast<size_t>(page) * ep.H + h) * ep.page_size + pos % ep.page_size) * ep.hd + e;
-                void* pool = (part == 1) ? ep.kpool : ep.vpool;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (pos[u] >= 0) ep.qbuf[static_cast<size_t>(row0 + u) * ep.d + cc] = sum[u] + bias;
+                return;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                page[u] = (pos[u] >= 0) ? ep.page_table[slot[u] * ep.max_pages + pos[u] / ep.page_size] : 0;
+            const int h = cc / ep.hd, e = cc - h * ep.hd;
+            void* pool = (part == 1) ? ep.kpool : ep.vpool;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pos[u] < 0) continue;
+                const size_t off = ((static_cast<size_t>(page[u]) * ep.H + h) * ep.page_size + pos[u] % ep.page_size) * ep.hd + e;
+                const float val = sum[u] + bias;
                 if (ep.kv_fp32) static_cast<float*>(pool)[off] = val;
                 else static_cast<__nv_bfloat16*>(pool)[off] = __float2bfloat16_rn(val);
             }
             break;
         }
         case EPI_RESID: {
-            float* p = ep.x + static_cast<size_t>(row) * ep.ld_out + m;
-            *p = *p + val;
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = (u < nrows) ? ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < nrows) ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] = xv[u] + (sum[u] + bias);
             break;
         }
         case EPI_ACT: {
-            float u = val;
-            if (ep.act_kind == 1) u = fmaxf(u, 0.f);
-            else if (ep.act_kind == 2) u = 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f));
-            __nv_bfloat16 hi, lo;
-            split_bf16(u, hi, lo);
-            ep.act[static_cast<size_t>(row) * ep.ld_out + m] = hi;
-            ep.act[static_cast<size_t>(row + ep.bpad_out) * ep.ld_out + m] = lo;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u >= nrows) continue;
+                float v = sum[u] + bias;
+                if (ep.act_kind == 1) v = fmaxf(v, 0.f);
+                else if (ep.act_kind == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+                __nv_bfloat16 hi, lo;
+                split_bf16(v, hi, lo);
+                ep.act[static_cast<size_t>(row0 + u) * ep.ld_out + m] = hi;
+                ep.act[static_cast<size_t>(row0 + u + ep.bpad_out) * ep.ld_out + m] = lo;
+            }
             break;
         }
         default:
-            ep.out[static_cast<size_t>(row) * ep.ld_out + ep.col_off + m] = val;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < nrows) ep.out[static_cast<size_t>(row0 + u) * ep.ld_out + ep.col_off + m] = sum[u] + bias;
     }
 }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const GemmEpilogue ep, int Nout, int total_kb, int kb_per_split, int b_col_off, int nvalid) {
+                  const GemmEpilogue ep, int Nout, int total_kb, int kb_per_split, int b_col_off, int nvalid,
+                  const void* pf_ptr, unsigned long long pf_bytes) {
     using L = GemmSmem<BN, STAGES>;
     constexpr int BPAD = BN / 2;
     extern __shared__ __align__(1024) uint8_t smem[];       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -115,7 +143,8 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int S = static_cast<int>(cluster_nctarank());      // K splits = cluster size
     const int z = static_cast<int>(cluster_ctarank());
-    const int m0 = (blockIdx.x / S) * GEMM_BM;
+    const int mt = blockIdx.x / S;                          // 128-feature tile
+    const int m0 = mt * GEMM_BM;
     const int kb0 = z * kb_per_split;
     const int nkb = max(0, min(kb_per_split, total_kb - kb0));
     const int pre = min(nkb, STAGES);
@@ -133,10 +162,13 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_fence_init();
         // Weights never depend on the previous kernel: their first STAGES tiles go in flight right away
         // (under PDL: while the producer grid is still draining); activations wait for griddepcontrol.wait.
+        const uint64_t pol = l2_policy_evict_first();      // weight tiles are read once per step
         for (int i = 0; i < pre; ++i) {
             mbar_arrive_expect_tx(&full_bar[i], L::STAGE_BYTES);
-            tma_load_2d(smem + i * L::STAGE_BYTES, &tmA, &full_bar[i], (kb0 + i) * GEMM_BK, m0);
+            tma_load_2d_hint(smem + i * L::STAGE_BYTES, &tmA, &full_bar[i], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
         }
+        // keep HBM busy across the kernel boundary: pull the NEXT GEMM's weights into L2 while this one runs
+        prefetch_l2_slice(pf_ptr, pf_bytes, blockIdx.x, gridDim.x);
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
@@ -156,11 +188,12 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_load_2d(smem + i * L::STAGE_BYTES + L::A_BYTES, &tmB, &full_bar[i],
                             b_col_off + (kb0 + i) * GEMM_BK, 0);
             int stage = 0, phase = 0;                       // state after the first `pre` fills
+            const uint64_t pol = l2_policy_evict_first();
             for (int i = pre; i < nkb; ++i) {
                 mbar_wait(&empty_bar[stage], phase);        // the MMA released this slot
                 mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                 uint8_t* a = smem + stage * L::STAGE_BYTES;
-                tma_load_2d(a, &tmA, &full_bar[stage], (kb0 + i) * GEMM_BK, m0);
+                tma_load_2d_hint(a, &tmA, &full_bar[stage], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
                 tma_load_2d(a + L::A_BYTES, &tmB, &full_bar[stage], b_col_off + (kb0 + i) * GEMM_BK, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -189,7 +222,8 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ===== epilogue part 1: TMEM -> registers -> reduce-scatter over the cluster (DSMEM) =========
         const int q = warp & 3;                             // TMEM lane quarter owned by this warp
         const int ml = q * 32 + lane;                       // feature inside the tile
-        const int R = BPAD / S;                             // token rows owned by each CTA of the cluster
+        const int R = BPAD / S;                             // token rows owned by each CTA (power of two)
+        const int shR = 31 - __clz(R);
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
@@ -217,14 +251,16 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < CH; ++j) {
                 const int row = c + j;
                 if (row < nvalid) {
-                    const int owner = row / R, rr = row - owner * R;
-                    st_dsmem_f32(red_addr + static_cast<uint32_t>(((z * R + rr) * GEMM_BM + ml) * 4), owner, hi[j] + lo[j]);
+                    const int owner = row >> shR, rr = row & (R - 1);
+                    st_dsmem_f32(red_addr + static_cast<uint32_t>(((((z << shR) + rr) << 7) + ml) << 2), owner, hi[j] + lo[j]);
                 }
             }
         }
         tc_fence_before();
+        if (threadIdx.x == 64) tl_mark(0x140 + ep.mode);
     }
     cluster_sync_all();                                     // all partials have landed in their owners' smem
+    if (threadIdx.x == 64) tl_mark(0x150 + ep.mode);
     if (warp >= 2) {
         // ===== epilogue part 2: fixed-order sum of the S partials of my R rows + fused epilogue =======
         const int q = warp & 3;
@@ -232,14 +268,23 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = m0 + ml;
         const int R = BPAD / S;
         if (m < Nout) {
-            for (int rr = 0; rr < R; ++rr) {
-                const int row = z * R + rr;
-                if (row >= nvalid) break;
-                float s = 0.f;
-                for (int zz = 0; zz < S; ++zz) s += red[(zz * R + rr) * GEMM_BM + ml];
-                apply_epilogue(ep, row, m, s);
+            const float bias = ep.bias[m];
+            for (int rr0 = 0; rr0 < R; rr0 += 4) {
+                const int row0 = z * R + rr0;
+                const int nrows = min(min(4, R - rr0), nvalid - row0);
+                if (nrows <= 0) break;
+                float sum[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float a = 0.f;
+                    if (u < nrows)
+                        for (int zz = 0; zz < S; ++zz) a += red[(zz * R + rr0 + u) * GEMM_BM + ml];
+                    sum[u] = a;
+                }
+                apply_epilogue4(ep, row0, nrows, m, sum, bias);
             }
         }
+        if (threadIdx.x == 64) tl_mark(0x160 + ep.mode);
     }
     __syncthreads();
     if (threadIdx.x == 0) tl_mark(0x130 + ep.mode);
@@ -259,6 +304,12 @@ void gemm_timeline_set(unsigned long long* buf, unsigned int* cnt) {
 // Selected with VCB_GEMM_IMPL=simt; never the default.  It exists so a tcgen05 descriptor bug can be told
 // apart from a bug anywhere else in the step.
 // ---------------------------------------------------------------------------------------------------
+// element (m, k) of the pre-tiled weight layout
+__host__ __device__ inline size_t packed_index(int m, int k, int Kdim) {
+    const int KB = Kdim / GEMM_BK;
+    return ((static_cast<size_t>(m / GEMM_BM) * KB + k / GEMM_BK) * GEMM_BM + (m % GEMM_BM)) * GEMM_BK + (k % GEMM_BK);
+}
+
 __global__ void gemm_w_xT_simt(const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ X,
                                const GemmEpilogue ep, int Nout, int Kdim, int ldx, int bpad, int b_col_off, int nvalid) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -267,20 +318,52 @@ __global__ void gemm_w_xT_simt(const __nv_bfloat16* __restrict__ W, const __nv_b
     for (int j = 0; j < nvalid; ++j) {
         float acc = 0.f;
         for (int k = lane; k < Kdim; k += 32) {
-            const float w = __bfloat162float(W[static_cast<size_t>(warp) * Kdim + k]);
+            const float w = __bfloat162float(W[packed_index(warp, k, Kdim)]);
             const float xh = __bfloat162float(X[static_cast<size_t>(j) * ldx + b_col_off + k]);
             const float xl = __bfloat162float(X[static_cast<size_t>(j + bpad) * ldx + b_col_off + k]);
             acc = fmaf(w, xh, acc);
             acc = fmaf(w, xl, acc);
         }
         acc = warp_sum(acc);
-        if (lane == 0) apply_epilogue(ep, j, warp, acc);
+        if (lane == 0) {
+            const float sum[4] = {acc, 0.f, 0.f, 0.f};
+            apply_epilogue4(ep, j, 1, warp, sum, ep.bias[warp]);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+// fp32 row-major [N, K] -> bf16 tiles [ceil(N/128)][K/64][128][64], rows beyond N zero-filled
+__global__ void pack_weight_tiles_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int Kdim) {
+    const size_t total = static_cast<size_t>((N + GEMM_BM - 1) / GEMM_BM) * GEMM_BM * Kdim;
+    const int KB = Kdim / GEMM_BK;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % GEMM_BK);
+        const int r = static_cast<int>((i / GEMM_BK) % GEMM_BM);
+        const size_t blk = i / (GEMM_BK * GEMM_BM);
+        const int kb = static_cast<int>(blk % KB);
+        const int mt = static_cast<int>(blk / KB);
+        const int m = mt * GEMM_BM + r, k = kb * GEMM_BK + c;
+        out[i] = (m < N) ? __float2bfloat16_rn(in[static_cast<size_t>(m) * Kdim + k]) : __float2bfloat16_rn(0.f);
+    }
+}
+
+size_t packed_weight_elems(int N, int Kdim) { return static_cast<size_t>((N + GEMM_BM - 1) / GEMM_BM) * GEMM_BM * Kdim; }
+
+int pack_weight(const float* w_f32_dev, __nv_bfloat16* out, int N, int Kdim, CUtensorMap* tm) {
+    if (Kdim % GEMM_BK) {
+        set_error("pack_weight: K=%d not a multiple of %d", Kdim, GEMM_BK);
+        return -1;
+    }
+    pack_weight_tiles_kernel<<<1024, 256>>>(w_f32_dev, out, N, Kdim);
+    VCB_CUDA_OK(cudaGetLastError());
+    const uint64_t rows = packed_weight_elems(N, Kdim) / GEMM_BK;       // 128-byte rows, 128 per tile
+    return make_tmap_bf16_2d(tm, out, rows, GEMM_BK, GEMM_BK, GEMM_BM);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -348,7 +431,7 @@ static int launch_one(const GemmCall& g, cudaStream_t st) {
     const int total_kb = g.Kdim / GEMM_BK;
     const int kbps = (total_kb + g.splits - 1) / g.splits;
     VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_w_xT_cluster<BN, STAGES>, *g.tmA, *g.tmB, g.ep, g.Nout, total_kb, kbps,
-                                   g.b_col_off, g.nvalid));
+                                   g.b_col_off, g.nvalid, g.pf_ptr, static_cast<unsigned long long>(g.pf_bytes)));
     return 0;
 }
 

@@ -7,8 +7,9 @@
 namespace vcb {
 
 static constexpr int KV_PAGE = 64;          // tokens per KV page
-static constexpr int ATT_THREADS = 128;
-static constexpr int ATT_STAGES = 2;
+static constexpr int ATT_CWARPS = 8;            // consumer warps per CTA
+static constexpr int ATT_THREADS = ATT_CWARPS * 32;
+static constexpr int ATT_STAGES = 3;
 
 __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
     v = warp_sum(v);
@@ -156,10 +157,10 @@ struct AttSmem {
     static constexpr int PAGE_BYTES = KV_PAGE * HD * sizeof(KVT);
     static constexpr int OFF_V = ATT_STAGES * PAGE_BYTES;
     static constexpr int OFF_SC = 2 * ATT_STAGES * PAGE_BYTES;
-    static constexpr int OFF_PW = OFF_SC + KV_PAGE * 4;
-    static constexpr int OFF_RED = OFF_PW + 4 * KV_PAGE * 4;
-    static constexpr int OFF_BAR = OFF_RED + 4 * HD * 4;
-    static constexpr int TOTAL = OFF_BAR + ATT_STAGES * 8 + 128;
+    static constexpr int OFF_PW = OFF_SC + 2 * KV_PAGE * 4;          // scores double-buffered by page parity
+    static constexpr int OFF_RED = OFF_PW + ATT_CWARPS * KV_PAGE * 4;
+    static constexpr int OFF_BAR = OFF_RED + ATT_CWARPS * HD * 4;
+    static constexpr int TOTAL = OFF_BAR + 2 * ATT_STAGES * 8 + 128;
 };
 
 template <typename KVT, int N>
@@ -194,12 +195,21 @@ __device__ __forceinline__ void load_kv_vec(const KVT* p, float (&out)[N]) {
     }
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Persistent, warp-specialised version: grid = a few CTAs per SM; each CTA walks a static list of work items
+// (row*head, context chunk).  Warp 4 is the TMA producer: it runs ahead ACROSS items, so the HBM stream never drains
+// at an item boundary (short CTAs with a cold start were the measured loss: 45% DRAM utilisation in ncu).
+// Warps 0..ATT_CWARPS-1 consume pages: scores -> online softmax -> PV, release the stage through an mbarrier.
 template <typename KVT, int HD>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS + 32)
 attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, const KVT* __restrict__ vpool,
                  const int* __restrict__ page_table, int max_pages, const int* __restrict__ row_slot,
                  const int* __restrict__ row_pos, int H, __nv_bfloat16* __restrict__ act, int ld_act, int bpad,
-                 float scale, float* __restrict__ ws, int* __restrict__ cnt, int maxch, int chunk_pages) {
+                 float scale, float* __restrict__ ws, int* __restrict__ cnt, int maxch, int chunk_pages, int n_rh,
+                 int n_chunks) {
     using L = AttSmem<KVT, HD>;
     constexpr int LPT = HD / 8;          // lanes per key in QK
     constexpr int TPW = 32 / LPT;        // keys per warp iteration
@@ -207,149 +217,185 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
     extern __shared__ __align__(128) uint8_t att_smem[];
     KVT* sK = reinterpret_cast<KVT*>(att_smem);
     KVT* sV = reinterpret_cast<KVT*>(att_smem + L::OFF_V);
-    float* sc = reinterpret_cast<float*>(att_smem + L::OFF_SC);
+    float* sc_all = reinterpret_cast<float*>(att_smem + L::OFF_SC);
     float* pw = reinterpret_cast<float*>(att_smem + L::OFF_PW);
     float* red = reinterpret_cast<float*>(att_smem + L::OFF_RED);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(att_smem + L::OFF_BAR);
+    uint64_t* full = reinterpret_cast<uint64_t*>(att_smem + L::OFF_BAR);
+    uint64_t* empty = full + ATT_STAGES;
     __shared__ int s_last;
 
-    const int rh = blockIdx.x;
-    const int r = rh / H, h = rh % H;
-    const int chunk = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ATT_STAGES; ++s) mbar_init(&bar[s], 1);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], ATT_CWARPS);
+        }
         mbar_fence_init();
+        tl_mark(0x300);
     }
-    if (threadIdx.x == 0) tl_mark(0x300);
+    __syncthreads();
     pdl_wait();
     if (threadIdx.x == 0) tl_mark(0x310);
-    const int pos = row_pos[r];
-    if (pos < 0) return;
-    const int npages = pos / KV_PAGE + 1;
-    const int nch = (npages + chunk_pages - 1) / chunk_pages;      // flash-decoding style split over the context
-    if (chunk >= nch) return;
-    const int p0 = chunk * chunk_pages;
-    const int p1 = min(npages, p0 + chunk_pages);
-    const int slot = row_slot[r];
-    const int* pt = page_table + slot * max_pages;
-    __syncthreads();
+    const int n_items = n_rh * n_chunks;
 
-    auto issue = [&](int p) {
-        const int s = (p - p0) % ATT_STAGES;
-        const size_t off = (static_cast<size_t>(pt[p]) * H + h) * KV_PAGE * HD;
-        mbar_arrive_expect_tx(&bar[s], 2 * L::PAGE_BYTES);
-        tma_bulk_g2s(sK + s * KV_PAGE * HD, kpool + off, L::PAGE_BYTES, &bar[s]);
-        tma_bulk_g2s(sV + s * KV_PAGE * HD, vpool + off, L::PAGE_BYTES, &bar[s]);
-    };
-    if (threadIdx.x == 0)
-        for (int p = p0; p < min(p1, p0 + ATT_STAGES); ++p) issue(p);
-
-    const int sub = lane % LPT;
-    float q[8];
-    {
-        const float* qp = qbuf + (static_cast<size_t>(r) * H + h) * HD + sub * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = qp[i];
-    }
-    float m_run = -INFINITY, l_run = 0.f;
-    float acc[DPT];
-#pragma unroll
-    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
-
-    for (int p = p0; p < p1; ++p) {
-        const int s = (p - p0) % ATT_STAGES;
-        mbar_wait(&bar[s], ((p - p0) / ATT_STAGES) & 1);
-        const KVT* K = sK + s * KV_PAGE * HD;
-        const KVT* V = sV + s * KV_PAGE * HD;
-        // ---- scores for this warp's 16 keys
-#pragma unroll
-        for (int it = 0; it < 16 / TPW; ++it) {
-            const int t = warp * 16 + it * TPW + lane / LPT;
-            float kv[8];
-            load_kv_vec<KVT, 8>(K + t * HD + sub * 8, kv);
-            float dsum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dsum = fmaf(q[i], kv[i], dsum);
-#pragma unroll
-            for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-            if (sub == 0) sc[t] = (p * KV_PAGE + t <= pos) ? dsum * scale : -INFINITY;
-        }
-        __syncthreads();
-        // ---- online softmax bookkeeping (every warp redundantly over all 64 scores: identical m, l)
-        const float s0 = sc[lane], s1 = sc[lane + 32];
-        const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
-        const float corr = expf(m_run - m_new);
-        const float p0_ = expf(s0 - m_new), p1_ = expf(s1 - m_new);
-        float* mypw = pw + warp * KV_PAGE;
-        mypw[lane] = p0_;
-        mypw[lane + 32] = p1_;
-        l_run = l_run * corr + warp_sum(p0_ + p1_);
-        m_run = m_new;
-        __syncwarp();
-        // ---- PV for this warp's 16 keys
-#pragma unroll
-        for (int i = 0; i < DPT; ++i) acc[i] *= corr;
-#pragma unroll 4
-        for (int tt = 0; tt < 16; ++tt) {
-            const int t = warp * 16 + tt;
-            const float pt_ = mypw[t];
-            float vv[DPT];
-            load_kv_vec<KVT, DPT>(V + t * HD + lane * DPT, vv);
-#pragma unroll
-            for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
-        }
-        __syncthreads();                                   // everyone is done with stage s
-        if (threadIdx.x == 0 && p + ATT_STAGES < p1) issue(p + ATT_STAGES);
-    }
-    if (threadIdx.x == 0) tl_mark(0x330);
-    // ---- combine the 4 warps' partial outputs
-#pragma unroll
-    for (int i = 0; i < DPT; ++i) red[warp * HD + lane * DPT + i] = acc[i];
-    __syncthreads();
-    const size_t ocol = static_cast<size_t>(h) * HD;
-    if (nch == 1) {
-        for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
-            const float o = (red[dd] + red[HD + dd] + red[2 * HD + dd] + red[3 * HD + dd]) / l_run;
-            __nv_bfloat16 hi, lo;
-            split_bf16(o, hi, lo);
-            act[static_cast<size_t>(r) * ld_act + ocol + dd] = hi;
-            act[static_cast<size_t>(r + bpad) * ld_act + ocol + dd] = lo;
+    if (warp == ATT_CWARPS) {
+        // ===== producer: one lane streams the K/V pages of every item of this CTA, in order ================
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();          // KV pages stream through L2 once per step
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int chunk = item / n_rh, rh = item - chunk * n_rh;
+                const int r = rh / H, h = rh - r * H;
+                const int pos = row_pos[r];
+                if (pos < 0) continue;
+                const int npages = pos / KV_PAGE + 1;
+                const int p0 = chunk * chunk_pages;
+                if (p0 >= npages) continue;
+                const int p1 = min(npages, p0 + chunk_pages);
+                const int* pt = page_table + row_slot[r] * max_pages;
+                for (int p = p0; p < p1; ++p, ++it) {
+                    const int s = it % ATT_STAGES;
+                    if (it >= ATT_STAGES) mbar_wait(&empty[s], ((it / ATT_STAGES) - 1) & 1);
+                    const size_t off = (static_cast<size_t>(pt[p]) * H + h) * KV_PAGE * HD;
+                    mbar_arrive_expect_tx(&full[s], 2 * L::PAGE_BYTES);
+                    tma_bulk_g2s_hint(sK + s * KV_PAGE * HD, kpool + off, L::PAGE_BYTES, &full[s], pol);
+                    tma_bulk_g2s_hint(sV + s * KV_PAGE * HD, vpool + off, L::PAGE_BYTES, &full[s], pol);
+                }
+            }
         }
         return;
     }
-    // ---- split context: publish (o, m, l); the last chunk to finish merges all chunks in chunk order
-    float* myws = ws + (static_cast<size_t>(rh) * maxch + chunk) * (HD + 2);
-    for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS)
-        myws[dd] = red[dd] + red[HD + dd] + red[2 * HD + dd] + red[3 * HD + dd];
-    if (threadIdx.x == 0) {
-        myws[HD] = m_run;
-        myws[HD + 1] = l_run;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&cnt[rh], 1) == nch - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const volatile float* base = ws + static_cast<size_t>(rh) * maxch * (HD + 2);
-    float M = -INFINITY;
-    for (int c = 0; c < nch; ++c) M = fmaxf(M, base[c * (HD + 2) + HD]);
-    for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
-        float Lsum = 0.f, O = 0.f;
-        for (int c = 0; c < nch; ++c) {
-            const float w = expf(base[c * (HD + 2) + HD] - M);
-            Lsum += base[c * (HD + 2) + HD + 1] * w;
-            O += base[c * (HD + 2) + dd] * w;
+
+    // ===== consumers ================================================================================
+    const int sub = lane % LPT;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / n_rh, rh = item - chunk * n_rh;
+        const int r = rh / H, h = rh - r * H;
+        const int pos = row_pos[r];
+        if (pos < 0) continue;
+        const int npages = pos / KV_PAGE + 1;
+        const int p0 = chunk * chunk_pages;
+        if (p0 >= npages) continue;
+        const int p1 = min(npages, p0 + chunk_pages);
+        const int nch = (npages + chunk_pages - 1) / chunk_pages;
+        float q[8];
+        {
+            const float* qp = qbuf + (static_cast<size_t>(r) * H + h) * HD + sub * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = qp[i];
         }
-        const float o = O / Lsum;
-        __nv_bfloat16 hi, lo;
-        split_bf16(o, hi, lo);
-        act[static_cast<size_t>(r) * ld_act + ocol + dd] = hi;
-        act[static_cast<size_t>(r + bpad) * ld_act + ocol + dd] = lo;
+        float m_run = -INFINITY, l_run = 0.f;
+        float acc[DPT];
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+
+        for (int p = p0; p < p1; ++p, ++it) {
+            const int s = it % ATT_STAGES;
+            mbar_wait(&full[s], (it / ATT_STAGES) & 1);
+            const KVT* K = sK + s * KV_PAGE * HD;
+            const KVT* V = sV + s * KV_PAGE * HD;
+            float* sc = sc_all + (it & 1) * KV_PAGE;
+            // ---- scores for this warp's KPW keys
+            constexpr int KPW = KV_PAGE / ATT_CWARPS;
+#pragma unroll
+            for (int itq = 0; itq < KPW / TPW; ++itq) {
+                const int t = warp * KPW + itq * TPW + lane / LPT;
+                float kv[8];
+                load_kv_vec<KVT, 8>(K + t * HD + sub * 8, kv);
+                float dsum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dsum = fmaf(q[i], kv[i], dsum);
+#pragma unroll
+                for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+                if (sub == 0) sc[t] = (p * KV_PAGE + t <= pos) ? dsum * scale : -INFINITY;
+            }
+            named_bar_sync(1, ATT_THREADS);
+            // ---- online softmax bookkeeping (every warp redundantly over all 64 scores: identical m, l)
+            const float s0 = sc[lane], s1 = sc[lane + 32];
+            const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
+            const float corr = expf(m_run - m_new);
+            const float e0 = expf(s0 - m_new), e1 = expf(s1 - m_new);
+            float* mypw = pw + warp * KV_PAGE;
+            mypw[lane] = e0;
+            mypw[lane + 32] = e1;
+            l_run = l_run * corr + warp_sum(e0 + e1);
+            m_run = m_new;
+            __syncwarp();
+            // ---- PV for this warp's KPW keys
+#pragma unroll
+            for (int i = 0; i < DPT; ++i) acc[i] *= corr;
+#pragma unroll
+            for (int tt = 0; tt < KPW; ++tt) {
+                const int t = warp * KPW + tt;
+                const float pt_ = mypw[t];
+                float vv[DPT];
+                load_kv_vec<KVT, DPT>(V + t * HD + lane * DPT, vv);
+#pragma unroll
+                for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);            // this warp is done with stage s
+        }
+        // ---- combine the 4 warps' partial outputs of this item
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) red[warp * HD + lane * DPT + i] = acc[i];
+        named_bar_sync(1, ATT_THREADS);
+        const size_t ocol = static_cast<size_t>(h) * HD;
+        if (nch == 1) {
+            for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
+                float osum = 0.f;
+#pragma unroll
+                for (int w = 0; w < ATT_CWARPS; ++w) osum += red[w * HD + dd];
+                const float o = osum / l_run;
+                __nv_bfloat16 hi, lo;
+                split_bf16(o, hi, lo);
+                act[static_cast<size_t>(r) * ld_act + ocol + dd] = hi;
+                act[static_cast<size_t>(r + bpad) * ld_act + ocol + dd] = lo;
+            }
+            named_bar_sync(1, ATT_THREADS);                   // red[] is reused by the next item
+            continue;
+        }
+        // ---- split context: publish (o, m, l); the last chunk to finish merges all chunks in chunk order
+        float* myws = ws + (static_cast<size_t>(rh) * maxch + chunk) * (HD + 2);
+        for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
+            float osum = 0.f;
+#pragma unroll
+            for (int w = 0; w < ATT_CWARPS; ++w) osum += red[w * HD + dd];
+            myws[dd] = osum;
+        }
+        if (threadIdx.x == 0) {
+            myws[HD] = m_run;
+            myws[HD + 1] = l_run;
+        }
+        __threadfence();
+        named_bar_sync(1, ATT_THREADS);
+        if (threadIdx.x == 0) s_last = (atomicAdd(&cnt[rh], 1) == nch - 1);
+        named_bar_sync(1, ATT_THREADS);
+        if (s_last) {
+            __threadfence();
+            const volatile float* base = ws + static_cast<size_t>(rh) * maxch * (HD + 2);
+            float M = -INFINITY;
+            for (int c = 0; c < nch; ++c) M = fmaxf(M, base[c * (HD + 2) + HD]);
+            for (int dd = threadIdx.x; dd < HD; dd += ATT_THREADS) {
+                float Lsum = 0.f, O = 0.f;
+                for (int c = 0; c < nch; ++c) {
+                    const float w = expf(base[c * (HD + 2) + HD] - M);
+                    Lsum += base[c * (HD + 2) + HD + 1] * w;
+                    O += base[c * (HD + 2) + dd] * w;
+                }
+                const float o = O / Lsum;
+                __nv_bfloat16 hi, lo;
+                split_bf16(o, hi, lo);
+                act[static_cast<size_t>(r) * ld_act + ocol + dd] = hi;
+                act[static_cast<size_t>(r + bpad) * ld_act + ocol + dd] = lo;
+            }
+            if (threadIdx.x == 0) cnt[rh] = 0;
+        }
+        named_bar_sync(1, ATT_THREADS);                       // s_last / red[] reused by the next item
     }
-    if (threadIdx.x == 0) cnt[rh] = 0;
+    if (threadIdx.x == 0) tl_mark(0x330);
 }
 
 // ---------------------------------------------------------------------------------------------------

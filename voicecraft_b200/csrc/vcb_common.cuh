@@ -102,6 +102,45 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
         : "memory");
 }
 
+// L2 cache policies / prefetch.  Streams that are touched once per step (KV pages, weight tiles) are loaded with
+// evict_first so they do not push the *prefetched* next-kernel weights out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+// asynchronous HBM -> L2 prefetch of a contiguous range (bytes % 16 == 0)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
+}
+// this CTA's share of a [ptr, ptr+bytes) range, issued by one thread in <= 32 KB pieces
+__device__ __forceinline__ void prefetch_l2_slice(const void* ptr, unsigned long long bytes, unsigned int part, unsigned int nparts) {
+    if (ptr == nullptr || bytes == 0) return;
+    unsigned long long chunk = ((bytes + nparts - 1) / nparts + 127ull) & ~127ull;
+    unsigned long long beg = chunk * part;
+    if (beg >= bytes) return;
+    unsigned long long end = beg + chunk < bytes ? beg + chunk : bytes;
+    const char* p = static_cast<const char*>(ptr);
+    for (unsigned long long o = beg; o < end; o += 32768ull) {
+        const unsigned long long n = (end - o < 32768ull ? end - o : 32768ull) & ~15ull;
+        if (n) tma_prefetch_l2(p + o, static_cast<uint32_t>(n));
+    }
+}
+
 // Optional device-side timeline (debug): CTA 0 of instrumented kernels appends (tag, globaltimer ns) records.
 // Each translation unit has its own copy of the pointer; the host sets them through vcb_timeline_set().
 static __device__ unsigned long long* g_tl_buf = nullptr;

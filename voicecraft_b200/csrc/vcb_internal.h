@@ -40,9 +40,13 @@ struct GemmCall {
     GemmEpilogue ep;
     int Nout = 0, Kdim = 0, ldx = 0, bpad = 0, splits = 1, b_col_off = 0, nvalid = 0;
     int pdl = 0, simt = 0, stages = 0;
+    const void* pf_ptr = nullptr;       // next GEMM's weights: prefetched into L2 while this kernel runs
+    size_t pf_bytes = 0;
 };
 int gemm_launch(const GemmCall& g, cudaStream_t st);
 int gemm_pick_splits(int Nout, int Kdim, int num_sms);
+size_t packed_weight_elems(int N, int Kdim);
+int pack_weight(const float* w_f32_dev, __nv_bfloat16* out, int N, int Kdim, CUtensorMap* tm);
 void gemm_timeline_set(unsigned long long* buf, unsigned int* cnt);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows);
