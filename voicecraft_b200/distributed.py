@@ -1,0 +1,60 @@
+"""Batch sharding by utterance across the GPUs of one node.
+
+The decode path has no cross-utterance dependency, so the multi-GPU story is: one process per GPU
+(torchrun), every rank holds a full weight replica and its own KV pool, utterances are partitioned across
+ranks, and there is NO collective inside the decode loop.  The only exchange is the final gather of the
+variable-length token matrices (padded all_gather over NCCL / NVLink; gloo in the CPU tests).
+The reference has no inference-side equivalent (single device, inference_tts_scale.py:42-105).
+"""
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def partition(lengths: Sequence[int], world_size: int, rank: int) -> List[int]:
+    """Indices of the utterances this rank decodes: longest-processing-time greedy over expected lengths, so the
+    slowest rank (which sets the wall time) is as short as possible.  Deterministic on every rank."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    loads = [0] * world_size
+    owner = [0] * len(lengths)
+    for i in order:
+        r = min(range(world_size), key=lambda q: (loads[q], q))
+        owner[i] = r
+        loads[r] += int(lengths[i])
+    return [i for i in range(len(lengths)) if owner[i] == rank]
+
+
+def gather_token_lists(local: List[torch.Tensor], local_ids: List[int], n_total: int, group=None) -> List[torch.Tensor]:
+    """All ranks end up with the full list (indexed by global utterance id) of [K, T_i] int64 token matrices.
+    Works on CPU tensors with gloo and CUDA tensors with NCCL."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out = [None] * n_total
+        for i, t in zip(local_ids, local):
+            out[i] = t
+        return out
+    world = dist.get_world_size(group)
+    dev = local[0].device if local else torch.device("cpu")
+    K = local[0].shape[0] if local else 0
+    meta = torch.tensor([len(local), K, max((t.shape[1] for t in local), default=0)], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    n_max = int(max(m[0] for m in metas))
+    K = int(max(m[1] for m in metas))
+    t_max = int(max(m[2] for m in metas))
+    pack = torch.full((n_max, K, t_max), -1, dtype=torch.int64, device=dev)
+    info = torch.full((n_max, 2), -1, dtype=torch.int64, device=dev)          # (global id, length)
+    for j, (i, t) in enumerate(zip(local_ids, local)):
+        pack[j, :, : t.shape[1]] = t
+        info[j, 0], info[j, 1] = i, t.shape[1]
+    packs = [torch.empty_like(pack) for _ in range(world)]
+    infos = [torch.empty_like(info) for _ in range(world)]
+    dist.all_gather(packs, pack, group=group)
+    dist.all_gather(infos, info, group=group)
+    out = [None] * n_total
+    for p, inf in zip(packs, infos):
+        for j in range(n_max):
+            gid, ln = int(inf[j, 0]), int(inf[j, 1])
+            if gid >= 0:
+                out[gid] = p[j, :, :ln].clone()
+    return out
