@@ -64,7 +64,7 @@ __device__ __forceinline__ void st_dsmem_f32(uint32_t local_smem_addr, uint32_t 
 // Fused epilogue for up to 4 token rows of one output feature m.  All loads of the group are issued before the first
 // dependent use (the per-row chains position -> page -> address would otherwise serialise on L2 latency).
 __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0, int nrows, int m, const float (&sum)[4],
-                                                float bias) {
+                                                float bias, float (&xnew)[4]) {
     switch (ep.mode) {
         case EPI_QKV: {
             int pos[4], slot[4], page[4];
@@ -100,8 +100,10 @@ __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0
 #pragma unroll
             for (int u = 0; u < 4; ++u) xv[u] = (u < nrows) ? ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] : 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (u < nrows) ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] = xv[u] + (sum[u] + bias);
+            for (int u = 0; u < 4; ++u) {
+                xnew[u] = xv[u] + (sum[u] + bias);
+                if (u < nrows) ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] = xnew[u];
+            }
             break;
         }
         case EPI_ACT: {
@@ -263,25 +265,84 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (threadIdx.x == 64) tl_mark(0x150 + ep.mode);
     if (warp >= 2) {
         // ===== epilogue part 2: fixed-order sum of the S partials of my R rows + fused epilogue =======
+        // scratch aliases pipeline stage 0: every TMA write / MMA read of this CTA's stages has retired (tmem_full), and
+        // peers only ever write into `red`.  (Static __shared__ here would cost the second resident CTA per SM.)
+        float* s_mean = reinterpret_cast<float*>(smem);
+        float* s_rstd = s_mean + GEMM_BM;
+        float (*s_part)[4][2] = reinterpret_cast<float (*)[4][2]>(s_rstd + GEMM_BM);
         const int q = warp & 3;
         const int ml = q * 32 + lane;
         const int m = m0 + ml;
         const int R = BPAD / S;
-        if (m < Nout) {
-            const float bias = ep.bias[m];
-            for (int rr0 = 0; rr0 < R; rr0 += 4) {
-                const int row0 = z * R + rr0;
-                const int nrows = min(min(4, R - rr0), nvalid - row0);
-                if (nrows <= 0) break;
-                float sum[4];
+        const bool valid_m = m < Nout;
+        pdl_wait();                                         // x / stats of earlier kernels are read below
+        if (ep.ln_fold) {
+            // mean / rstd of my rows from the per-tile partial sums the producer kernel left (fixed tile order)
+            for (int rr = ml; rr < R; rr += GEMM_BM) {
+                const int row = z * R + rr;
+                float mean = 0.f, rstd = 0.f;
+                if (row < nvalid) {
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int t = 0; t < ep.stats_tiles; ++t) {
+                        s1 += ep.stats[(static_cast<size_t>(t) * STATS_ROWS + row) * 2];
+                        s2 += ep.stats[(static_cast<size_t>(t) * STATS_ROWS + row) * 2 + 1];
+                    }
+                    mean = s1 * ep.inv_d;
+                    rstd = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - mean * mean, 0.f) + ep.ln_eps);
+                }
+                s_mean[rr] = mean;
+                s_rstd[rr] = rstd;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        const float bias = valid_m ? ep.bias[m] : 0.f;
+        const float cv = (ep.ln_fold && valid_m) ? ep.cvec[m] : 0.f;
+        const float gnext = (ep.emit && valid_m) ? ep.next_gamma[m] : 0.f;
+        for (int rr0 = 0; rr0 < R; rr0 += 4) {
+            const int row0 = z * R + rr0;
+            const int nrows = min(min(4, R - rr0), nvalid - row0);
+            if (nrows <= 0) break;
+            float sum[4], xnew[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float a = 0.f;
+                if (u < nrows) {
+                    for (int zz = 0; zz < S; ++zz) a += red[(zz * R + rr0 + u) * GEMM_BM + ml];
+                    if (ep.ln_fold) a = s_rstd[rr0 + u] * (a - s_mean[rr0 + u] * cv);
+                }
+                sum[u] = a;
+            }
+            if (valid_m) apply_epilogue4(ep, row0, nrows, m, sum, bias, xnew);
+            if (ep.emit) {
+                // next GEMM's operand gamma_next * x_new (hi/lo) and this tile's (sum x, sum x^2) per row
+                float p1[4], p2[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    float a = 0.f;
-                    if (u < nrows)
-                        for (int zz = 0; zz < S; ++zz) a += red[(zz * R + rr0 + u) * GEMM_BM + ml];
-                    sum[u] = a;
+                    const bool ok = valid_m && u < nrows;
+                    if (ok) {
+                        __nv_bfloat16 hi, lo;
+                        split_bf16(gnext * xnew[u], hi, lo);
+                        ep.next_act[static_cast<size_t>(row0 + u) * ep.next_ld + m] = hi;
+                        ep.next_act[static_cast<size_t>(row0 + u + ep.next_bpad) * ep.next_ld + m] = lo;
+                    }
+                    p1[u] = warp_sum(ok ? xnew[u] : 0.f);
+                    p2[u] = warp_sum(ok ? xnew[u] * xnew[u] : 0.f);
                 }
-                apply_epilogue4(ep, row0, nrows, m, sum, bias);
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        s_part[q][u][0] = p1[u];
+                        s_part[q][u][1] = p2[u];
+                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (ml < 8) {
+                    const int u = ml >> 1, w = ml & 1;
+                    if (u < nrows)
+                        ep.stats_out[(static_cast<size_t>(mt) * STATS_ROWS + row0 + u) * 2 + w] =
+                            s_part[0][u][w] + s_part[1][u][w] + s_part[2][u][w] + s_part[3][u][w];
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
             }
         }
         if (threadIdx.x == 64) tl_mark(0x160 + ep.mode);
@@ -326,8 +387,28 @@ __global__ void gemm_w_xT_simt(const __nv_bfloat16* __restrict__ W, const __nv_b
         }
         acc = warp_sum(acc);
         if (lane == 0) {
+            if (ep.ln_fold) {
+                float s1 = 0.f, s2 = 0.f;
+                for (int t = 0; t < ep.stats_tiles; ++t) {
+                    s1 += ep.stats[(static_cast<size_t>(t) * STATS_ROWS + j) * 2];
+                    s2 += ep.stats[(static_cast<size_t>(t) * STATS_ROWS + j) * 2 + 1];
+                }
+                const float mean = s1 * ep.inv_d;
+                const float rstd = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - mean * mean, 0.f) + ep.ln_eps);
+                acc = rstd * (acc - mean * ep.cvec[warp]);
+            }
             const float sum[4] = {acc, 0.f, 0.f, 0.f};
-            apply_epilogue4(ep, j, 1, warp, sum, ep.bias[warp]);
+            float xnew[4];
+            apply_epilogue4(ep, j, 1, warp, sum, ep.bias[warp], xnew);
+            if (ep.emit) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(ep.next_gamma[warp] * xnew[0], hi, lo);
+                ep.next_act[static_cast<size_t>(j) * ep.next_ld + warp] = hi;
+                ep.next_act[static_cast<size_t>(j + ep.next_bpad) * ep.next_ld + warp] = lo;
+                // one "tile" per feature group of 128, accumulated with atomics (cross-check path only)
+                atomicAdd(&ep.stats_out[(static_cast<size_t>(warp / GEMM_BM) * STATS_ROWS + j) * 2], xnew[0]);
+                atomicAdd(&ep.stats_out[(static_cast<size_t>(warp / GEMM_BM) * STATS_ROWS + j) * 2 + 1], xnew[0] * xnew[0]);
+            }
         }
     }
 }
@@ -349,6 +430,34 @@ __global__ void pack_weight_tiles_kernel(const float* __restrict__ in, __nv_bflo
         const int m = mt * GEMM_BM + r, k = kb * GEMM_BK + c;
         out[i] = (m < N) ? __float2bfloat16_rn(in[static_cast<size_t>(m) * Kdim + k]) : __float2bfloat16_rn(0.f);
     }
+}
+
+// LayerNorm folding vectors from the (bf16, pre-tiled) weight: cvec[m] = sum_k gamma[k] W[m,k],
+// bprime[m] = bias[m] + sum_k beta[k] W[m,k]; one warp per output feature, fp32.
+__global__ void ln_fold_vectors_kernel(const __nv_bfloat16* __restrict__ Wp, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ bias,
+                                       float* __restrict__ cvec, float* __restrict__ bprime, int N, int Kdim) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (m >= N) return;
+    float c = 0.f, b = 0.f;
+    for (int k = lane; k < Kdim; k += 32) {
+        const float w = __bfloat162float(Wp[packed_index(m, k, Kdim)]);
+        c = fmaf(gamma[k], w, c);
+        b = fmaf(beta[k], w, b);
+    }
+    c = warp_sum(c);
+    b = warp_sum(b);
+    if (lane == 0) {
+        cvec[m] = c;
+        bprime[m] = bias[m] + b;
+    }
+}
+
+int ln_fold_vectors(const __nv_bfloat16* Wp, const float* gamma, const float* beta, const float* bias, float* cvec,
+                    float* bprime, int N, int Kdim) {
+    ln_fold_vectors_kernel<<<(N * 32 + 255) / 256, 256>>>(Wp, gamma, beta, bias, cvec, bprime, N, Kdim);
+    VCB_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 size_t packed_weight_elems(int N, int Kdim) { return static_cast<size_t>((N + GEMM_BM - 1) / GEMM_BM) * GEMM_BM * Kdim; }

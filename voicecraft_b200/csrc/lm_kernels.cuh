@@ -402,10 +402,12 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
 // Step prologue: assign each row its position, advance the per-slot counters, fetch the input embedding
 // produced by the previous sampler call.
 // ---------------------------------------------------------------------------------------------------
-__global__ void step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ st,
-                                 const GroupState* __restrict__ gr, int* __restrict__ row_slot,
-                                 int* __restrict__ row_pos, int* __restrict__ row_last,
-                                 const float* __restrict__ x_slot, float* __restrict__ x_rows, int d) {
+__global__ void __launch_bounds__(256)
+step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ st, const GroupState* __restrict__ gr,
+                 int* __restrict__ row_slot, int* __restrict__ row_pos, int* __restrict__ row_last,
+                 const float* __restrict__ x_slot, float* __restrict__ x_rows, int d,
+                 const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats) {
+    __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x;
@@ -425,8 +427,28 @@ __global__ void step_prep_kernel(const int* __restrict__ slots, int n, SlotState
     }
     __syncthreads();
     if (s_pos < 0) return;
-    for (int c = threadIdx.x; c < d; c += blockDim.x)
-        x_rows[static_cast<size_t>(r) * d + c] = x_slot[static_cast<size_t>(slot) * d + c];
+    // x row + (LayerNorm folding) gamma0 * x as hi/lo rows and the row statistics for layer 0's QKV GEMM
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float v = x_slot[static_cast<size_t>(slot) * d + c];
+        x_rows[static_cast<size_t>(r) * d + c] = v;
+        if (gamma0) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(gamma0[c] * v, hi, lo);
+            act[static_cast<size_t>(r) * d + c] = hi;
+            act[static_cast<size_t>(r + bpad) * d + c] = lo;
+            s1 += v;
+            s2 += v * v;
+        }
+    }
+    if (gamma0) {
+        s1 = block_sum_256(s1, red);
+        s2 = block_sum_256(s2, red);
+        if (threadIdx.x == 0) {
+            stats[static_cast<size_t>(r) * 2] = s1;
+            stats[static_cast<size_t>(r) * 2 + 1] = s2;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -609,14 +631,34 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                int left = s_kleft, b = 255;
-                for (; b > 0; --b) {
-                    if (hist[b] >= left) break;
-                    left -= hist[b];
+            if (warp == 0) {
+                // descending scan over the 256 bins: lane l owns bins [255-8l-7, 255-8l]
+                int loc[8], lsum = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    loc[u] = hist[255 - 8 * lane - u];
+                    lsum += loc[u];
                 }
-                s_kleft = left;
-                s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+                int incl = lsum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int left0 = s_kleft;
+                const int before = incl - lsum;                     // keys in higher bins than this lane's
+                const unsigned hit = __ballot_sync(0xffffffffu, incl >= left0);
+                const int owner = hit ? __ffs(hit) - 1 : 31;
+                if (lane == owner) {
+                    int left = left0 - before, b = 255 - 8 * lane;
+                    for (int u = 0; u < 7; ++u) {
+                        if (loc[u] >= left) break;
+                        left -= loc[u];
+                        --b;
+                    }
+                    s_kleft = left;
+                    s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+                }
             }
             __syncthreads();
         }

@@ -30,7 +30,19 @@ struct GemmEpilogue {
     __nv_bfloat16* act = nullptr;
     float* out = nullptr;
     int ld_out = 0, col_off = 0, act_kind = 0, bpad_out = 0;
+    // LayerNorm folded into this GEMM (the B operand is gamma*x, not LN(x)):
+    //   y = rstd[row] * (acc - mean[row] * cvec[m]) + bias[m]   with bias := b + W.beta, cvec := W.gamma   
+    int ln_fold = 0, stats_tiles = 0;
+    const float* cvec = nullptr;
+    const float* stats = nullptr;         // [tile][STATS_ROWS][2] partial (sum x, sum x^2) written by the producer
+    float inv_d = 0.f, ln_eps = 1e-5f;
+    // EPI_RESID producer side: also emit gamma_next * x_new as hi/lo rows + this tile's row statistics
+    int emit = 0, next_ld = 0, next_bpad = 0;
+    const float* next_gamma = nullptr;
+    __nv_bfloat16* next_act = nullptr;
+    float* stats_out = nullptr;
 };
+static constexpr int STATS_ROWS = 128;
 
 struct GemmCall {
     const CUtensorMap* tmA = nullptr;   // weights [Nout, Kdim]
@@ -47,6 +59,8 @@ int gemm_launch(const GemmCall& g, cudaStream_t st);
 int gemm_pick_splits(int Nout, int Kdim, int num_sms);
 size_t packed_weight_elems(int N, int Kdim);
 int pack_weight(const float* w_f32_dev, __nv_bfloat16* out, int N, int Kdim, CUtensorMap* tm);
+int ln_fold_vectors(const __nv_bfloat16* Wp, const float* gamma, const float* beta, const float* bias, float* cvec,
+                    float* bprime, int N, int Kdim);
 void gemm_timeline_set(unsigned long long* buf, unsigned int* cnt);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows);
