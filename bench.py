@@ -282,8 +282,11 @@ def main():
                 bytes_per_launch = Wb / (cnt[0] / nprof)                          # mean weight bytes per GEMM launch
             dur = msb[dom] / cnt[dom] * 1e-3
             ach = bytes_per_launch / dur / 1e9
+            # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_summary.md): the GEMMs
+            # move exactly their weight bytes, attention 1.09x its algorithmic KV bytes
+            traffic = bytes_per_launch * (1.09 if dom == 1 else 1.0)
             roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": dur * 1e6,
+                    "traffic": traffic, "traffic_source": "profiles/r01_ncu_summary.md (dram__bytes_read+write per launch / algorithmic)", "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": dur * 1e6,
                     "peak_source": peak_src, "ctx": S_prof, "by_kernel": shares,
                     "note": "per-launch CUDA events serialise launches; shares, not absolutes, compare with ncu"}
     sess.close()
@@ -312,6 +315,9 @@ def main():
                "d2h_bytes_per_step": d2h / max(steps_e2e, 1), "seconds": dt, "generated_frames": gen_frames,
                "note": "prefill + all decode steps + polling + H2D of prompts + D2H of tokens inside the timed region"}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cb = None
