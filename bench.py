@@ -235,6 +235,7 @@ def main():
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
     launches = lib.vcb_counter(eng, b"launches") - launches0
+    chain_info = {"clusters": int(lib.vcb_counter(eng, b"chain_clusters")), "epoch": int(lib.vcb_counter(eng, b"chain_epoch"))}
     st = sess.poll()
     assert all(s.n_steps == 1 + W + Ksteps for s in st), [s.n_steps for s in st]
     assert not any(s.done for s in st)
@@ -328,7 +329,7 @@ def main():
             "steps": Ksteps, "warmup": W, "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(args, cfg), ctx_start=ctx0, ctx_end=ctx1),
             "rtf_per_stream": frames_s / (world * B) / cfg.encodec_sr, "frames_per_s": frames_s,
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "step_roofline": step_roof,
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "gemm_chain": chain_info, "roofline": roof, "step_roofline": step_roof,
             "cpu_baseline": cb}
     print(json.dumps(line))
 

@@ -9,6 +9,6 @@ python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/sw_*.json')):
     try:
-        d=json.load(open(f)); print(f, round(d['value']), round(d['ms_per_step'],3))
+        d=json.load(open(f)); print(f, round(d['value']), round(d['ms_per_step'],3), d.get('gemm_chain'), d['gpu_launches'])
     except Exception as e: print(f,'ERR', open(f.replace('.json','.err')).read()[-300:])
 PY

@@ -113,3 +113,21 @@ def test_generator_stream_matches_torch_multinomial_on_device():
     for _ in range(m.last_stats["steps"]):
         torch.empty(K, V, device="cuda").exponential_(1)
     assert torch.equal(after, torch.empty(4, device="cuda").exponential_(1))
+
+
+def test_chain_path_bpad32_matches_oracle():
+    """Best-of-20 on the 512-d model: 20 rows -> Bpad 32, i.e. the persistent GEMM-chain kernel with 4 rows per CTA
+    (the fixtures only reach Bpad 16).  Oracle with the same rounding policy and the same noise."""
+    from oracle import lm_oracle
+    from voicecraft_b200 import synthetic
+    cfg = synthetic.make_config("small")
+    sd = synthetic.make_state_dict(cfg, seed=31)
+    x, x_lens, y = synthetic.synthetic_utterance(cfg, 77, text_len=4, prompt_frames=10)
+    kw = dict(top_k=30, top_p=0.9, temperature=1.0, stop_repetition=3, silence_tokens=gu.SILENCE, kvcache=1)
+    ores = lm_oracle.OracleLM(cfg, sd, kv_round_bf16=True).inference_tts_batch(
+        x, x_lens, y, batch_size=20, noise_fn=gu.cpu_noise_fn(3), **kw)[0]
+    m = _model(cfg, sd, "bf16")
+    m.configure_engine(max_slots=24, max_seq_len=512, kv_dtype="bf16")
+    m.noise_fn = gu.cpu_noise_fn(3)
+    res = m.inference_tts_batch(x.cuda(), x_lens.cuda(), y.cuda(), batch_size=20, **kw)[0]
+    assert np.array_equal(res.cpu().numpy(), ores.numpy())
