@@ -66,7 +66,7 @@ typedef struct {
 
 /* Per-slot status returned by vcb_poll. */
 typedef struct {
-    int32_t done;      /* generation finished (all codebooks ended, all spans) */
+    int32_t done;      /* 1: generation finished (all codebooks ended, all spans); 2: stopped, token-log / KV capacity exhausted */
     int32_t forced;    /* >0: the next decode step feeds a forced embedding and consumes no noise */
     int32_t n_steps;   /* sampling steps recorded so far */
     int32_t keep;      /* best-of-N: member index whose tokens are the result (-1 while undecided) */

@@ -131,3 +131,38 @@ def test_chain_path_bpad32_matches_oracle():
     m.noise_fn = gu.cpu_noise_fn(3)
     res = m.inference_tts_batch(x.cuda(), x_lens.cuda(), y.cuda(), batch_size=20, **kw)[0]
     assert np.array_equal(res.cpu().numpy(), ores.numpy())
+
+
+def test_batched_sessions_match_single_calls():
+    """inference_tts_many / inference_many (independent utterances in one batch) return, row by row, what the reference-shaped
+    single calls return when each row is fed the same noise rows."""
+    from voicecraft_b200 import synthetic
+    cfg = synthetic.make_config("tiny")
+    sd = synthetic.make_state_dict(cfg, seed=41)
+    sd["predict_layer.0.2.bias"][cfg.eog] += 3.0
+    m = _model(cfg, sd, "bf16")
+    K, V = cfg.n_codebooks, 2048 + cfg.n_special
+    utts = [synthetic.synthetic_utterance(cfg, 500 + i, text_len=5 + i, prompt_frames=30 + 3 * i) for i in range(3)]
+    spans = [torch.tensor([[[5, 9]]]), torch.tensor([[[4, 8], [15, 20]]]), torch.tensor([[[10, 12]]])]
+    kw = dict(top_k=1, top_p=1.0, temperature=1.0)      # greedy: independent of how noise rows are batched
+    singles_tts = [m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), stop_repetition=3, **kw)[0] for x, xl, y in utts]
+    many_tts = m.inference_tts_many([u[0] for u in utts], [u[2] for u in utts], poll_every=1, stop_repetition=3, **kw)
+    for a, (b, _) in zip(singles_tts, many_tts):
+        assert torch.equal(a, b)
+    singles_ed = [m.inference(x.cuda(), xl.cuda(), y.cuda(), sp.cuda(), **kw) for (x, xl, y), sp in zip(utts, spans)]
+    many_ed = m.inference_many([u[0] for u in utts], [u[2] for u in utts], spans, poll_every=1, **kw)
+    for a, b in zip(singles_ed, many_ed):
+        assert torch.equal(a, b)
+
+
+def test_capacity_exhaustion_is_reported():
+    from voicecraft_b200 import synthetic, _lib
+    cfg = synthetic.make_config("tiny")
+    sd = synthetic.make_state_dict(cfg, seed=42)
+    end = cfg.eos
+    sd["predict_layer.0.2.bias"][end] = -1e4
+    m = _model(cfg, sd, "bf16")
+    m.configure_engine(max_new_tokens=16, max_seq_len=512)
+    x, xl, y = synthetic.synthetic_utterance(cfg, 9, text_len=8, prompt_frames=10)
+    with pytest.raises(_lib.VcbError):
+        m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), top_k=10)

@@ -558,6 +558,7 @@ int launch_sampler(vcb_engine* e, int n, const float* noise, const vcb_sampling*
     a.dbg_logits = e->dbg_logits;
     a.tok_log = e->tok_log;
     a.max_steps = e->cfg.max_new_tokens;
+    a.max_seq = e->cfg.max_seq_len;
     a.x_slot = e->x_slot;
     a.E_audio = e->d_E_audio;
     a.mask_emb = e->mask_emb;

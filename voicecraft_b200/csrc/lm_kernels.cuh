@@ -478,7 +478,7 @@ struct SamplerArgs {
     const float* noise;       // [n*K][V]
     float* dbg_logits;        // [n*K][V] or null
     int* tok_log;             // [max_slots][max_steps][K]
-    int max_steps;
+    int max_steps, max_seq;
     float* x_slot;            // [max_slots][d]
     const float* const* E_audio;
     const float* mask_emb;
@@ -845,6 +845,10 @@ __device__ void sampler_finish_slot(const SamplerArgs& a, int slot, float* sred)
     }
     G.trig_keep = 0;
     G.cur_num_gen += 1;
+    if (S.n_steps >= a.max_steps - 1 || S.seq_len >= a.max_seq - 2) {     // token log / KV capacity exhausted: stop, flag it
+        G.done = 2;
+        return;
+    }
     if (G.n_eog == K) {                                                                      // span finished
         if (G.n_spans_done < 8) G.span_ends[G.n_spans_done] = S.n_steps;
         G.n_spans_done += 1;

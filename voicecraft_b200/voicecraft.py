@@ -291,6 +291,9 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         steps = 1
         while True:
             _lib.check(lib.vcb_poll(eng, c_slots, n, status, stream))
+            if any(s.done == 2 for s in status):
+                raise _lib.VcbError("decode stopped: engine capacity (max_new_tokens / max_seq_len) exhausted; "
+                                    "raise it with configure_engine()")
             if all(s.done for s in status):
                 break
             if max_steps is not None and steps >= max_steps:
@@ -497,6 +500,27 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
     # Not a reference API: the reference decodes one utterance per call.  Each utterance keeps its own
     # state machine; one Exp(1) draw of shape [B*K, V] per step feeds all of them.
     # ------------------------------------------------------------------------------------------------
+    def open_edit_session(self, xs, ys, mask_intervals, top_k=-100, top_p=1.0, temperature=1.0, stop_repetition=-1,
+                          silence_tokens=(1388, 1898, 131)):
+        """Independent speech-editing utterances decoded as one batch (BASELINE config 3).  mask_intervals: list of
+        [1,M,2] tensors.  Returns a DecodeSession; results() gives the edited [1,K,T'] per utterance."""
+        return DecodeSession(self, xs, ys, self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens),
+                             mask_intervals=mask_intervals)
+
+    @torch.no_grad()
+    def inference_many(self, xs, ys, mask_intervals, poll_every: int = 4, **kw):
+        """Batched counterpart of `inference` (speech editing) for independent utterances."""
+        sess = self.open_edit_session(xs, ys, mask_intervals, **kw)
+        try:
+            sess.sample()
+            while True:
+                if sess.steps % poll_every == 0 and sess.all_done():
+                    break
+                sess.step()
+            return [r[0] for r in sess.results()]
+        finally:
+            sess.close()
+
     def open_tts_session(self, xs, ys, top_k=-100, top_p=1.0, temperature=1.0, stop_repetition=3,
                          silence_tokens=(1388, 1898, 131)):
         """xs: list of [1,L] int64, ys: list of [1,T,K] int64 (any device).  Prefills every utterance (one packed,
@@ -521,8 +545,10 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
 class DecodeSession:
     """A batch of independent TTS utterances resident in the engine (slots 0..B-1)."""
 
-    def __init__(self, model: "VoiceCraft", xs, ys, sp):
+    def __init__(self, model: "VoiceCraft", xs, ys, sp, mask_intervals=None):
         a = model.args
+        self.edit = mask_intervals is not None
+        self.non_mask = []
         K = a.n_codebooks
         dev = model.mask_embedding.device
         self.model, self.sp, self.dev, self.K = model, sp, dev, K
@@ -536,22 +562,36 @@ class DecodeSession:
             y = y.to(dev, non_blocking=True)
             if a.special_first:
                 y = y + int(a.n_special)
-            yk = y.transpose(2, 1)[0].long()
-            shifted, _ = model.shift([[yk]])
-            prompt = shifted[0][0][:, : -(K - 1)] if K > 1 else shifted[0][0]
-            y_tok = prompt.transpose(1, 0).contiguous()
+            yk = y.transpose(2, 1)[0].long().contiguous()
+            idx = len(prompts)
+            if self.edit:
+                spans = [(int(s), int(e)) for s, e in mask_intervals[idx][0].tolist()]
+                y_tok, mask_rows, more_vals, non_mask = model._edit_prompt(yk, spans)
+                self.non_mask.append(non_mask)
+                cap = int(x.shape[1]) * 10
+                extra = (K + 3) * (len(spans) + 1)
+            else:
+                shifted, _ = model.shift([[yk]])
+                prompt = shifted[0][0][:, : -(K - 1)] if K > 1 else shifted[0][0]
+                y_tok = prompt.transpose(1, 0).contiguous()
+                mask_rows, more_vals = None, []
+                cap = int(x.shape[1]) * (int(a.encodec_sr) // 5)
+                extra = K
             x_ids = x[0].long().contiguous()
-            keep_alive += [y_tok, x_ids]
+            keep_alive += [y_tok, x_ids, mask_rows]
             self.y0.append(yk)
-            cap = int(x.shape[1]) * (int(a.encodec_sr) // 5)
-            need_seq = max(need_seq, int(x.shape[1]) + max(int(y_tok.shape[0]), cap + 1) + K + 8)
-            prompts.append((int(x.shape[1]), x_ids, int(y_tok.shape[0]), y_tok))
+            need_seq = max(need_seq, int(x.shape[1]) + max(int(y_tok.shape[0]), cap + 1) + extra + 8)
+            prompts.append((int(x.shape[1]), x_ids, int(y_tok.shape[0]), y_tok, mask_rows, more_vals))
         self.eng = model._engine(need_slots=self.B, need_seq=need_seq)
         self.V = model.n_audio_tokens[0]
         P = (_lib.vcb_prompt * self.B)()
-        for i, (xl, x_ids, yl, y_tok) in enumerate(prompts):
-            P[i] = _lib.vcb_prompt(slot=i, n_copies=1, mode=0, x_len=xl, text_ids_dev=x_ids.data_ptr(), y_len=yl,
-                                   y_tokens_dev=y_tok.data_ptr(), mask_rows_dev=None, n_more_spans=0)
+        for i, (xl, x_ids, yl, y_tok, mask_rows, more_vals) in enumerate(prompts):
+            P[i] = _lib.vcb_prompt(slot=i, n_copies=1, mode=1 if self.edit else 0, x_len=xl, text_ids_dev=x_ids.data_ptr(),
+                                   y_len=yl, y_tokens_dev=y_tok.data_ptr(),
+                                   mask_rows_dev=mask_rows.data_ptr() if mask_rows is not None else None,
+                                   n_more_spans=len(more_vals))
+            for j, v in enumerate(more_vals):
+                P[i].more_mask_rows[j] = int(v)
         self.c_slots = (C.c_int32 * self.B)(*range(self.B))
         self.status = (_lib.vcb_status * self.B)()
         self.noise = torch.empty(self.B * K, self.V, device=dev, dtype=torch.float32)
@@ -569,6 +609,7 @@ class DecodeSession:
         self.steps += 1
 
     def step(self):
+        # edit sessions: forced hand-over steps of individual utterances simply ignore their noise rows
         self.model._draw_noise(self.noise)
         _lib.check(self.lib.vcb_decode_step(self.eng, self.c_slots, self.B, self.noise.data_ptr(), C.byref(self.sp),
                                             self.stream))
@@ -579,7 +620,11 @@ class DecodeSession:
         return self.status
 
     def all_done(self):
-        return all(s.done for s in self.poll())
+        st = self.poll()
+        if any(s.done == 2 for s in st):
+            raise _lib.VcbError("decode stopped: engine capacity (max_new_tokens / max_seq_len) exhausted; "
+                                "raise it with configure_engine()")
+        return all(s.done for s in st)
 
     def raw_tokens(self, i):
         """delayed token rows [n_steps, K] of utterance i (host numpy)"""
@@ -592,6 +637,20 @@ class DecodeSession:
         st = self.poll()
         for i in range(self.B):
             rows = self.model._read_rows(self.eng, i, st[i].n_steps, self.stream)
+            if self.edit:
+                assert st[i].done, "edit session results() needs finished utterances"
+                ends = [st[i].span_ends[j] for j in range(st[i].n_spans_done)]
+                pieces, lo = [], 0
+                for (s0, s1), hi in zip(self.non_mask[i], ends):
+                    pieces.append(self.y0[i][:, s0:s1])
+                    pieces.append(torch.from_numpy(VoiceCraft._undelay(rows[lo:hi], self.K)).to(self.dev))
+                    lo = hi
+                pieces.append(self.y0[i][:, self.non_mask[i][-1][0]: self.non_mask[i][-1][1]])
+                res = torch.cat(pieces, dim=1).unsqueeze(0)
+                if a.special_first:
+                    res = res - int(a.n_special)
+                out.append((res, None))
+                continue
             if st[i].done:
                 gen = torch.from_numpy(VoiceCraft._undelay(rows, self.K)).to(self.dev)
             else:       # truncated session: drop the still-delayed tail
