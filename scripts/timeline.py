@@ -21,10 +21,18 @@ lib.vcb_timeline(0, buf, 65536, C.byref(n))
 recs = sorted(((buf[2*i+1], buf[2*i]) for i in range(n.value)))
 t0 = recs[0][0]
 names = {0x100:"gemm.start",0x110:"gemm.waited",0x120:"gemm.acc_ready",0x130:"gemm.end",0x140:"gemm.dsmem_sent",0x150:"gemm.cluster_synced",0x160:"gemm.epi_done",0x200:"ln.start",0x210:"ln.waited",0x230:"ln.end",
-         0x300:"attn.start",0x310:"attn.waited",0x330:"attn.end",0x400:"samp.start",0x410:"samp.waited"}
+         0x300:"attn.start",0x310:"attn.waited",0x330:"attn.end",0x400:"samp.start",0x410:"samp.waited",0x430:"samp.finish_slot_done"}
 modes = ["qkv","resid","act","logits"]
-for t, tag in recs[: 120]:
+def name(tag):
     base = tag & ~0xf if (tag & 0xf00) == 0x100 else tag
     nm = names.get(base, hex(tag))
     if (tag & 0xf00) == 0x100: nm += "." + modes[tag & 0xf]
-    print(f"{(t - t0)/1000:10.2f} us  {nm}")
+    return nm
+for t, tag in recs[: 120]:
+    print(f"{(t - t0)/1000:10.2f} us  {name(tag)}")
+# the step boundary: last layers -> heads -> sampler -> next step's first kernels
+idx = [i for i, (t, tag) in enumerate(recs) if tag == 0x400]
+if idx:
+    print("---- around the first sampler ----")
+    for t, tag in recs[max(0, idx[0] - 40): idx[0] + 25]:
+        print(f"{(t - t0)/1000:10.2f} us  {name(tag)}")

@@ -64,7 +64,7 @@ __device__ __forceinline__ void st_dsmem_f32(uint32_t local_smem_addr, uint32_t 
 // Fused epilogue for up to 4 token rows of one output feature m.  All loads of the group are issued before the first
 // dependent use (the per-row chains position -> page -> address would otherwise serialise on L2 latency).
 __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0, int nrows, int m, const float (&sum)[4],
-                                                float bias, float (&xnew)[4]) {
+                                                float bias, float (&xnew)[4], int colx = 0) {
     switch (ep.mode) {
         case EPI_QKV: {
             int pos[4], slot[4], page[4];
@@ -123,7 +123,7 @@ __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0
         default:
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (u < nrows) ep.out[static_cast<size_t>(row0 + u) * ep.ld_out + ep.col_off + m] = sum[u] + bias;
+                if (u < nrows) ep.out[static_cast<size_t>(row0 + u) * ep.ld_out + ep.col_off + colx + m] = sum[u] + bias;
     }
 }
 
@@ -131,7 +131,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmEpilogue ep, int Nout, int total_kb, int kb_per_split, int b_col_off, int nvalid,
-                  const void* pf_ptr, unsigned long long pf_bytes) {
+                  const void* pf_ptr, unsigned long long pf_bytes, const GemmGroup grp) {
     using L = GemmSmem<BN, STAGES>;
     constexpr int BPAD = BN / 2;
     extern __shared__ __align__(1024) uint8_t smem[];       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -147,6 +147,11 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int z = static_cast<int>(cluster_ctarank());
     const int mt = blockIdx.x / S;                          // 128-feature tile
     const int m0 = mt * GEMM_BM;
+    // grouped launch (blockIdx.y = group): same shapes, per-group weight map / bias / column offsets (the K logit heads)
+    const int grp_i = blockIdx.y;
+    const CUtensorMap* pA = grp.tmA ? grp.tmA + grp_i : &tmA;
+    b_col_off += grp_i * grp.b_stride;
+    const int colx = grp_i * grp.col_stride;
     const int kb0 = z * kb_per_split;
     const int nkb = max(0, min(kb_per_split, total_kb - kb0));
     const int pre = min(nkb, STAGES);
@@ -154,7 +159,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     pdl_launch_dependents();        // dependents may be scheduled now; their griddepcontrol.wait still orders the data
     if (threadIdx.x == 0) tl_mark(0x100 + ep.mode);
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(pA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -167,7 +172,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint64_t pol = l2_policy_evict_first();      // weight tiles are read once per step
         for (int i = 0; i < pre; ++i) {
             mbar_arrive_expect_tx(&full_bar[i], L::STAGE_BYTES);
-            tma_load_2d_hint(smem + i * L::STAGE_BYTES, &tmA, &full_bar[i], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
+            tma_load_2d_hint(smem + i * L::STAGE_BYTES, pA, &full_bar[i], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
         }
         // keep HBM busy across the kernel boundary: pull the NEXT GEMM's weights into L2 while this one runs
         prefetch_l2_slice(pf_ptr, pf_bytes, blockIdx.x, gridDim.x);
@@ -195,7 +200,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&empty_bar[stage], phase);        // the MMA released this slot
                 mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                 uint8_t* a = smem + stage * L::STAGE_BYTES;
-                tma_load_2d_hint(a, &tmA, &full_bar[stage], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
+                tma_load_2d_hint(a, pA, &full_bar[stage], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
                 tma_load_2d(a + L::A_BYTES, &tmB, &full_bar[stage], b_col_off + (kb0 + i) * GEMM_BK, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -295,7 +300,8 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
         }
-        const float bias = valid_m ? ep.bias[m] : 0.f;
+        const float* bias_ptr = grp.bias ? grp.bias[grp_i] : ep.bias;
+        const float bias = valid_m ? bias_ptr[m] : 0.f;
         const float cv = (ep.ln_fold && valid_m) ? ep.cvec[m] : 0.f;
         const float gnext = (ep.emit && valid_m) ? ep.next_gamma[m] : 0.f;
         for (int rr0 = 0; rr0 < R; rr0 += 4) {
@@ -312,7 +318,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 sum[u] = a;
             }
-            if (valid_m) apply_epilogue4(ep, row0, nrows, m, sum, bias, xnew);
+            if (valid_m) apply_epilogue4(ep, row0, nrows, m, sum, bias, xnew, colx);
             if (ep.emit) {
                 // next GEMM's operand gamma_next * x_new (hi/lo) and this tile's (sum x, sum x^2) per row
                 float p1[4], p2[4];
@@ -524,7 +530,7 @@ static int launch_one(const GemmCall& g, cudaStream_t st) {
     }
     const int tiles = (g.Nout + GEMM_BM - 1) / GEMM_BM;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(tiles * g.splits, 1, 1);
+    cfg.gridDim = dim3(tiles * g.splits, g.grp.tmA ? g.groups : 1, 1);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
@@ -540,7 +546,7 @@ static int launch_one(const GemmCall& g, cudaStream_t st) {
     const int total_kb = g.Kdim / GEMM_BK;
     const int kbps = (total_kb + g.splits - 1) / g.splits;
     VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_w_xT_cluster<BN, STAGES>, *g.tmA, *g.tmB, g.ep, g.Nout, total_kb, kbps,
-                                   g.b_col_off, g.nvalid, g.pf_ptr, static_cast<unsigned long long>(g.pf_bytes)));
+                                   g.b_col_off, g.nvalid, g.pf_ptr, static_cast<unsigned long long>(g.pf_bytes), g.grp));
     return 0;
 }
 

@@ -65,6 +65,7 @@ struct vcb_engine {
     std::vector<Matrix> h2;                       // predict_layer.{k}.2  [V, Hh]
     float *b_h1 = nullptr;                        // [K*Hh]
     float **d_bias2 = nullptr;                    // device array of K pointers
+    CUtensorMap* d_h2_maps = nullptr;             // device array of the K second-stage weight maps (grouped launch)
     float **d_E_audio = nullptr;                  // device array of K pointers
     float *E_text = nullptr, *mask_emb = nullptr, *pe = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
     float alpha_t = 1.f, alpha_a = 1.f;
@@ -532,14 +533,43 @@ int sample_rows(vcb_engine* e, int n, const float* h_src, const int* h_index, co
     ea.bpad_out = bpad;
     if (run_gemm(e, e->h1, &e->tm_act_d[bi], e->act_d, m.d, bpad, n, 0, m.d, ea, st, &e->h2[0])) return -1;
     const int ldl = m.K * m.Vpad;
-    for (int k = 0; k < m.K; ++k) {
-        GemmEpilogue el;
-        el.mode = EPI_LOGITS;
-        el.bias = e->h_bias2[k];
-        el.out = e->logits;
-        el.ld_out = ldl;
-        el.col_off = k * m.Vpad;
-        if (run_gemm(e, e->h2[k], &e->tm_act_h[bi], e->act_h, KH, bpad, n, k * m.Hh, m.Hh, el, st, k + 1 < m.K ? &e->h2[k + 1] : &e->layers[0].qkv)) return -1;
+    if (!e->opt_simt) {
+        // the K second-stage heads as ONE grouped launch (blockIdx.y = codebook)
+        GemmCall g;
+        g.tmA = &e->h2[0].tm;
+        g.tmB = &e->tm_act_h[bi];
+        g.ep.mode = EPI_LOGITS;
+        g.ep.bias = e->h_bias2[0];
+        g.ep.out = e->logits;
+        g.ep.ld_out = ldl;
+        g.Nout = m.V;
+        g.Kdim = m.Hh;
+        g.ldx = KH;
+        g.bpad = bpad;
+        g.splits = gemm_pick_splits(m.V, m.Hh, e->num_sms / std::max(1, m.K));
+        while (g.splits > 1 && bpad % g.splits) g.splits /= 2;
+        g.nvalid = n;
+        g.pdl = e->opt_pdl;
+        g.grp.tmA = e->d_h2_maps;
+        g.grp.bias = e->d_bias2;
+        g.grp.b_stride = m.Hh;
+        g.grp.col_stride = m.Vpad;
+        g.groups = m.K;
+        LAUNCH_COUNT(e);
+        ProfScope ps(e, PC_GEMM, st);
+        if (gemm_launch(g, st)) return -1;
+    } else {
+        for (int k = 0; k < m.K; ++k) {
+            GemmEpilogue el;
+            el.mode = EPI_LOGITS;
+            el.bias = e->h_bias2[k];
+            el.out = e->logits;
+            el.ld_out = ldl;
+            el.col_off = k * m.Vpad;
+            if (run_gemm(e, e->h2[k], &e->tm_act_h[bi], e->act_h, KH, bpad, n, k * m.Hh, m.Hh, el, st,
+                         k + 1 < m.K ? &e->h2[k + 1] : &e->layers[0].qkv))
+                return -1;
+        }
     }
     return launch_sampler(e, n, noise, sp, st);
 }
@@ -672,7 +702,7 @@ int vcb_destroy(vcb_engine* e) {
     }
     cudaFree(e->h1.w);
     for (auto& M : e->h2) cudaFree(M.w);
-    void* ptrs[] = {e->b_h1, e->d_bias2, e->d_E_audio, e->pe, e->x_rows, e->qbuf, e->logits, e->att_ws, e->att_cnt, e->ln_stats, e->chain_ctr, e->x_slot, e->h_slot,
+    void* ptrs[] = {e->b_h1, e->d_h2_maps, e->d_bias2, e->d_E_audio, e->pe, e->x_rows, e->qbuf, e->logits, e->att_ws, e->att_cnt, e->ln_stats, e->chain_ctr, e->x_slot, e->h_slot,
                     e->act_d, e->act_d2, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->all_rows, e->page_table,
                     e->d_slots, e->tok_log, e->dbg_logits, e->st, e->gr, e->d_seqs};
     for (void* p : ptrs) cudaFree(p);
@@ -802,6 +832,12 @@ int vcb_finalize_weights(vcb_engine* e) {
         if (!e->d_bias2) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_bias2), m.K * sizeof(float*)));
         if (!e->d_E_audio) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_E_audio), m.K * sizeof(float*)));
         e->h_bias2 = b2;
+        {
+            std::vector<CUtensorMap> maps(m.K);
+            for (int k = 0; k < m.K; ++k) maps[k] = e->h2[k].tm;
+            if (!e->d_h2_maps) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_h2_maps), m.K * sizeof(CUtensorMap)));
+            VCB_CUDA_OK(cudaMemcpy(e->d_h2_maps, maps.data(), m.K * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+        }
         VCB_CUDA_OK(cudaMemcpy(e->d_bias2, b2.data(), m.K * sizeof(float*), cudaMemcpyHostToDevice));
         VCB_CUDA_OK(cudaMemcpy(e->d_E_audio, ea.data(), m.K * sizeof(float*), cudaMemcpyHostToDevice));
     }

@@ -802,6 +802,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
     if (!s_flag) return;
     __threadfence();
     sampler_finish_slot(a, slot, sred);
+    if (threadIdx.x == 0) tl_mark(0x430);
 }
 
 // Last codebook row of a slot: next input embedding + silence bookkeeping; last slot of a group: group state.

@@ -61,6 +61,13 @@ struct ChainArgs {
 int chain_launch(const ChainArgs& args, int bpad, int nclusters, int pdl, cudaStream_t st);
 int chain_max_clusters(int bpad);
 
+// Grouped launch of gemm_w_xT_cluster (blockIdx.y = group): weight tensor maps in a device array, per-group bias pointers.
+struct GemmGroup {
+    const CUtensorMap* tmA = nullptr;     // device array [groups]; null = plain launch
+    const float* const* bias = nullptr;   // device array [groups]
+    int b_stride = 0, col_stride = 0;     // added per group to the activation column offset / output column offset
+};
+
 struct GemmCall {
     const CUtensorMap* tmA = nullptr;   // weights [Nout, Kdim]
     const CUtensorMap* tmB = nullptr;   // activations [2*bpad, ldx]
@@ -69,6 +76,8 @@ struct GemmCall {
     GemmEpilogue ep;
     int Nout = 0, Kdim = 0, ldx = 0, bpad = 0, splits = 1, b_col_off = 0, nvalid = 0;
     int pdl = 0, simt = 0, stages = 0;
+    GemmGroup grp;
+    int groups = 1;
     const void* pf_ptr = nullptr;       // next GEMM's weights: prefetched into L2 while this kernel runs
     size_t pf_bytes = 0;
 };
