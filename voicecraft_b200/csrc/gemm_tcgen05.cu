@@ -185,6 +185,18 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     cluster_sync_all();             // CTA-wide sync + "every CTA of the cluster has started" (required before DSMEM)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // per-feature epilogue constants (bias / LN-fold vector / next gamma) are model weights, never written by a kernel:
+    // the epilogue warps fetch them while the mainloop runs, off the critical tail
+    float w_bias = 0.f, w_cv = 0.f, w_gnext = 0.f;
+    if (warp >= 2) {
+        const int m = m0 + (warp & 3) * 32 + lane;
+        if (m < Nout) {
+            const float* bias_ptr = grp.bias ? grp.bias[grp_i] : ep.bias;
+            w_bias = bias_ptr[m];
+            if (ep.ln_fold) w_cv = ep.cvec[m];
+            if (ep.emit) w_gnext = ep.next_gamma[m];
+        }
+    }
 
     if (warp == 0) {
         // ===== TMA producer ==========================================================================
@@ -300,10 +312,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
         }
-        const float* bias_ptr = grp.bias ? grp.bias[grp_i] : ep.bias;
-        const float bias = valid_m ? bias_ptr[m] : 0.f;
-        const float cv = (ep.ln_fold && valid_m) ? ep.cvec[m] : 0.f;
-        const float gnext = (ep.emit && valid_m) ? ep.next_gamma[m] : 0.f;
+        const float bias = w_bias, cv = w_cv, gnext = w_gnext;
         for (int rr0 = 0; rr0 < R; rr0 += 4) {
             const int row0 = z * R + rr0;
             const int nrows = min(min(4, R - rr0), nvalid - row0);
