@@ -233,6 +233,9 @@ int run_gemm(vcb_engine* e, const Matrix& W, const CUtensorMap* tmB, const __nv_
     g.ldx = ldx;
     g.bpad = bpad;
     g.splits = gemm_pick_splits(W.rows, kdim, e->num_sms);
+    // >= 64 rows: the per-CTA epilogue / DSMEM exchange grows with the rows, so half the cluster size wins
+    // (scripts/bench_gemm.py at B = 64 / 128: QKV 22.4 -> 17.5 us, out 16.4 -> 10.9, FFN1 23.0 -> 18.0, FFN2 25.4 -> 19.7 at B = 64)
+    if (bpad >= 64 && g.splits > 1) g.splits /= 2;
     if (e->opt_gemm_maxctas > 0) {          // experiment knob: keep every GEMM to one CTA per SM (PDL ping-pong)
         const int tiles = (W.rows + 127) / 128;
         while (g.splits > 1 && tiles * g.splits > e->opt_gemm_maxctas) g.splits /= 2;

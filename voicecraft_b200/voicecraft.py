@@ -150,7 +150,7 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         self._eng_key = None
         self._eng_opts = dict(max_slots=8, max_seq_len=2048, max_new_tokens=4096, kv_dtype="bf16")
         self.noise_fn = None          # optional: callable(shape, device) -> fp32 Exp(1) tensor on `device`
-        self.poll_every = 1
+        self.poll_every = 4           # inference_tts*: poll the done flag every N steps (device generator only)
         self.last_stats = {}
         self.trace_logits = None      # set to a list to collect the raw logits [n*K, V] of every sampling step
 
@@ -270,8 +270,12 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             patterns.append(pats)
         return shifted_y, patterns
 
-    def _run(self, eng, slots, n_rows, sp, stream, max_steps=None):
-        """prefill is done; run sample / decode_step until every listed slot's group is done."""
+    def _run(self, eng, slots, n_rows, sp, stream, max_steps=None, speculative=False):
+        """prefill is done; run sample / decode_step until every listed slot's group is done.
+
+        speculative (TTS with the device generator only): poll every `poll_every` steps instead of every step.  Steps
+        issued after the group finished are no-ops on the device, but each consumed one [n*K,V] draw of the generator;
+        the surplus is handed back by rewinding the Philox offset, so the generator ends exactly where the reference's would."""
         lib = _lib.load()
         a = self.args
         dev = self.mask_embedding.device
@@ -285,26 +289,34 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
                 t = torch.empty(n_rows * K, V, device=dev, dtype=torch.float32)
                 _lib.check(lib.vcb_debug_logits(eng, t.data_ptr(), n_rows * K))
                 self.trace_logits.append(t)
+        every = max(1, int(self.poll_every)) if (speculative and self.noise_fn is None and self.trace_logits is None) else 1
+        gen = torch.cuda.default_generators[dev.index or 0] if every > 1 else None
+        off0 = gen.get_offset() if gen is not None else 0
         self._draw_noise(noise)
+        delta = (gen.get_offset() - off0) if gen is not None else 0      # generator advance per draw of this shape
         _lib.check(lib.vcb_sample(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
         trace()
         steps = 1
         while True:
-            _lib.check(lib.vcb_poll(eng, c_slots, n, status, stream))
-            if any(s.done == 2 for s in status):
-                raise _lib.VcbError("decode stopped: engine capacity (max_new_tokens / max_seq_len) exhausted; "
-                                    "raise it with configure_engine()")
-            if all(s.done for s in status):
-                break
+            if steps % every == 0 or every == 1:
+                _lib.check(lib.vcb_poll(eng, c_slots, n, status, stream))
+                if any(s.done == 2 for s in status):
+                    raise _lib.VcbError("decode stopped: engine capacity (max_new_tokens / max_seq_len) exhausted; "
+                                        "raise it with configure_engine()")
+                if all(s.done for s in status):
+                    break
             if max_steps is not None and steps >= max_steps:
                 break
-            forced = any(s.forced for s in status)
+            forced = every == 1 and any(s.forced for s in status)
             if not forced:                               # forced hand-over steps consume no random numbers
                 self._draw_noise(noise)
             _lib.check(lib.vcb_decode_step(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
             if not forced:
                 trace()
             steps += 1
+        if gen is not None and delta > 0:
+            used = max(int(s.n_steps) for s in status)                # sampling steps the reference would have drawn for
+            gen.set_offset(off0 + used * delta)
         return status
 
     def _read_rows(self, eng, slot, n_steps, stream):
@@ -368,7 +380,7 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             try:
                 _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))
                 slots = list(range(n_copies))
-                status = self._run(eng, slots, n_copies, sp, stream)
+                status = self._run(eng, slots, n_copies, sp, stream, speculative=True)
                 keep = status[0].keep if n_copies > 1 else 0
                 rows = self._read_rows(eng, keep, status[keep].n_steps, stream)
             finally:
