@@ -300,7 +300,7 @@ def main():
         torch.manual_seed(1 + rank)
         barrier()
         t0 = time.perf_counter()
-        out = model.inference_tts_many(xs_h, ys_h, poll_every=16, **kw)
+        out = model.inference_tts_many(xs_h, ys_h, poll_every=8, **kw)
         res_h = [r[0].cpu() for r in out]
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0

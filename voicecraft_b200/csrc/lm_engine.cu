@@ -1083,16 +1083,21 @@ int vcb_poll(vcb_engine* e, const int32_t* slots, int32_t n, vcb_status* out, vo
             return -1;
         }
     }
+    // two bulk copies of the (small) state tables instead of two copies per slot
+    static thread_local std::vector<SlotState> hs;
+    static thread_local std::vector<GroupState> hg;
+    hs.resize(e->cfg.max_slots);
+    hg.resize(e->cfg.max_slots);
+    VCB_CUDA_OK(cudaMemcpy(hs.data(), e->st, hs.size() * sizeof(SlotState), cudaMemcpyDeviceToHost));
+    VCB_CUDA_OK(cudaMemcpy(hg.data(), e->gr, hg.size() * sizeof(GroupState), cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {
         const int slot = slots[i];
         if (slot < 0 || slot >= e->cfg.max_slots || e->slot_group[slot] < 0) {
             set_error("slot %d is not open", slot);
             return -1;
         }
-        SlotState S;
-        GroupState G;
-        VCB_CUDA_OK(cudaMemcpy(&S, e->st + slot, sizeof(S), cudaMemcpyDeviceToHost));
-        VCB_CUDA_OK(cudaMemcpy(&G, e->gr + e->slot_group[slot], sizeof(G), cudaMemcpyDeviceToHost));
+        const SlotState& S = hs[slot];
+        const GroupState& G = hg[e->slot_group[slot]];
         out[i].done = G.done;
         out[i].forced = S.forced;
         out[i].n_steps = S.n_steps;
