@@ -24,6 +24,8 @@
 #include "vcb_internal.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace vcb {
 
@@ -39,7 +41,7 @@ struct GemmSmem {
     static constexpr int RED_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int RED_BYTES = (BN / 2) * GEMM_BM * 4;          // [S][R][128] fp32 with S*R = Bpad
     static constexpr int BAR_OFFSET = RED_OFFSET + RED_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 2) * 8 + 8;       // full[S] empty[S] tmem_full red_full + tmem slot
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -55,10 +57,29 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void st_dsmem_f32(uint32_t local_smem_addr, uint32_t cta, float v) {
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+    return remote;
+}
+// Asynchronous store into a peer CTA's shared memory that counts its bytes on the peer's mbarrier: the owner of the
+// rows learns that every partial has landed from its own barrier -- no cluster-wide barrier (and no GPU-scope
+// membar, which is what barrier.cluster.arrive.release costs) between the accumulators and the epilogue.
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, uint32_t remote_bar, float v) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_addr), "f"(v),
+                 "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_f32x4(uint32_t remote_addr, uint32_t remote_bar, float a, float b, float c, float d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     remote_addr),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(remote_bar)
+                 : "memory");
+}
+// bounded wait: a byte-count mismatch would otherwise hang the GPU; ~1 s of polling, then trap (surfaces as a CUDA error)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    for (unsigned int spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
 }
 
 // Fused epilogue for up to 4 token rows of one output feature m.  All loads of the group are issued before the first
@@ -139,7 +160,8 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* red_full = tmem_full + 1;                     // all S partials of my R rows have landed in `red`
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -157,7 +179,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pre = min(nkb, STAGES);
 
     pdl_launch_dependents();        // dependents may be scheduled now; their griddepcontrol.wait still orders the data
-    if (threadIdx.x == 0) tl_mark(0x100 + ep.mode);
+    if (threadIdx.x == 0) { tl_mark(0x100 + ep.mode); tl_mark_all(0x100 + ep.mode); }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(pA);
         tma_prefetch_desc(&tmB);
@@ -166,7 +188,10 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
+        mbar_init(red_full, 1);
         mbar_fence_init();
+        // every CTA of the cluster sends all of my R rows x 128 features (fp32), armed before anyone can send
+        mbar_arrive_expect_tx(red_full, static_cast<uint32_t>(BPAD) * GEMM_BM * 4);
         // Weights never depend on the previous kernel: their first STAGES tiles go in flight right away
         // (under PDL: while the producer grid is still draining); activations wait for griddepcontrol.wait.
         const uint64_t pol = l2_policy_evict_first();      // weight tiles are read once per step
@@ -175,14 +200,15 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d_hint(smem + i * L::STAGE_BYTES, pA, &full_bar[i], 0, (mt * total_kb + kb0 + i) * GEMM_BM, pol);
         }
         // keep HBM busy across the kernel boundary: pull the NEXT GEMM's weights into L2 while this one runs
-        prefetch_l2_slice(pf_ptr, pf_bytes, blockIdx.x, gridDim.x);
+        // (bit 63 of pf_bytes: issue it after this CTA's last weight load instead -- HBM idles during the epilogue)
+        if (!(pf_bytes >> 63)) prefetch_l2_slice(pf_ptr, pf_bytes, blockIdx.x, gridDim.x);
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
         tmem_relinquish();
     }
     tc_fence_before();
-    cluster_sync_all();             // CTA-wide sync + "every CTA of the cluster has started" (required before DSMEM)
+    cluster_sync_all();             // CTA-wide sync + "every CTA of the cluster has started and armed its barrier"
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // per-feature epilogue constants (bias / LN-fold vector / next gamma) are model weights, never written by a kernel:
@@ -203,6 +229,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             pdl_wait();
             tl_mark(0x110 + ep.mode);
+            tl_mark_all(0x110 + ep.mode);
             for (int i = 0; i < pre; ++i)
                 tma_load_2d(smem + i * L::STAGE_BYTES + L::A_BYTES, &tmB, &full_bar[i],
                             b_col_off + (kb0 + i) * GEMM_BK, 0);
@@ -216,6 +243,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_load_2d(a + L::A_BYTES, &tmB, &full_bar[stage], b_col_off + (kb0 + i) * GEMM_BK, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (pf_bytes >> 63) prefetch_l2_slice(pf_ptr, pf_bytes & ~(1ull << 63), blockIdx.x, gridDim.x);
         }
     } else if (warp == 1) {
         // ===== MMA issuer ============================================================================
@@ -250,7 +278,10 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (threadIdx.x == 64) tl_mark(0x120 + ep.mode);
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const uint32_t red_addr = smem_u32(red);
+        const uint32_t bar_addr = smem_u32(red_full);
         constexpr int CH = BPAD < 32 ? 16 : 32;
+        // red layout in the owner: [writer z][feature ml][R rows] -- a thread's R partials for one owner are contiguous
+        // (16-byte vector stores when R >= 4).  All Bpad rows are sent, valid or not: the byte count is a constant.
 #pragma unroll 1
         for (int c = 0; c < BPAD; c += CH) {
             float hi[CH], lo[CH];
@@ -267,20 +298,29 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int j = 0; j < CH; ++j) hi[j] = lo[j] = 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
+            for (int j = 0; j < CH; j += 4) {
                 const int row = c + j;
-                if (row < nvalid) {
+                if (R >= 4) {
                     const int owner = row >> shR, rr = row & (R - 1);
-                    st_dsmem_f32(red_addr + static_cast<uint32_t>(((((z << shR) + rr) << 7) + ml) << 2), owner, hi[j] + lo[j]);
+                    const uint32_t off = static_cast<uint32_t>((((z << 7) + ml) << shR) + rr) << 2;
+                    st_async_f32x4(mapa_u32(red_addr + off, owner), mapa_u32(bar_addr, owner), hi[j] + lo[j],
+                                   hi[j + 1] + lo[j + 1], hi[j + 2] + lo[j + 2], hi[j + 3] + lo[j + 3]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int owner = (row + u) >> shR, rr = (row + u) & (R - 1);
+                        const uint32_t off = static_cast<uint32_t>((((z << 7) + ml) << shR) + rr) << 2;
+                        st_async_f32(mapa_u32(red_addr + off, owner), mapa_u32(bar_addr, owner), hi[j + u] + lo[j + u]);
+                    }
                 }
             }
         }
         tc_fence_before();
         if (threadIdx.x == 64) tl_mark(0x140 + ep.mode);
     }
-    cluster_sync_all();                                     // all partials have landed in their owners' smem
-    if (threadIdx.x == 64) tl_mark(0x150 + ep.mode);
     if (warp >= 2) {
+        mbar_wait_bounded(red_full, 0);                     // all S partials of my rows have landed (async stores counted)
+        if (threadIdx.x == 64) tl_mark(0x150 + ep.mode);
         // ===== epilogue part 2: fixed-order sum of the S partials of my R rows + fused epilogue =======
         // scratch aliases pipeline stage 0: every TMA write / MMA read of this CTA's stages has retired (tmem_full), and
         // peers only ever write into `red`.  (Static __shared__ here would cost the second resident CTA per SM.)
@@ -299,10 +339,20 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int row = z * R + rr;
                 float mean = 0.f, rstd = 0.f;
                 if (row < nvalid) {
+                    // 16 tiles = one batch of independent 8-byte loads (a single L2 round trip), summed in tile order
                     float s1 = 0.f, s2 = 0.f;
-                    for (int t = 0; t < ep.stats_tiles; ++t) {
-                        s1 += ep.stats[(static_cast<size_t>(t) * STATS_ROWS + row) * 2];
-                        s2 += ep.stats[(static_cast<size_t>(t) * STATS_ROWS + row) * 2 + 1];
+                    for (int t0 = 0; t0 < ep.stats_tiles; t0 += 16) {
+                        float2 v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            v[i] = (t0 + i < ep.stats_tiles)
+                                       ? *reinterpret_cast<const float2*>(ep.stats + (static_cast<size_t>(t0 + i) * STATS_ROWS + row) * 2)
+                                       : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            s1 += v[i].x;
+                            s2 += v[i].y;
+                        }
                     }
                     mean = s1 * ep.inv_d;
                     rstd = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - mean * mean, 0.f) + ep.ln_eps);
@@ -322,7 +372,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int u = 0; u < 4; ++u) {
                 float a = 0.f;
                 if (u < nrows) {
-                    for (int zz = 0; zz < S; ++zz) a += red[(zz * R + rr0 + u) * GEMM_BM + ml];
+                    for (int zz = 0; zz < S; ++zz) a += red[(zz * GEMM_BM + ml) * R + rr0 + u];
                     if (ep.ln_fold) a = s_rstd[rr0 + u] * (a - s_mean[rr0 + u] * cv);
                 }
                 sum[u] = a;
@@ -363,7 +413,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (threadIdx.x == 64) tl_mark(0x160 + ep.mode);
     }
     __syncthreads();
-    if (threadIdx.x == 0) tl_mark(0x130 + ep.mode);
+    if (threadIdx.x == 0) { tl_mark(0x130 + ep.mode); tl_mark_all(0x130 + ep.mode); }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
@@ -536,6 +586,11 @@ static int launch_one(const GemmCall& g, cudaStream_t st) {
         VCB_CUDA_OK(cudaFuncSetAttribute(gemm_w_xT_cluster<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::TOTAL));
         attr_set = true;
+        if (getenv("VCB_DEBUG_OCC")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_w_xT_cluster<BN, STAGES>, GEMM_THREADS, L::TOTAL);
+            fprintf(stderr, "[vcb] gemm<%d,%d>: %d B smem, %d CTAs/SM (occupancy API)\n", BN, STAGES, L::TOTAL, nb);
+        }
     }
     const int tiles = (g.Nout + GEMM_BM - 1) / GEMM_BM;
     cudaLaunchConfig_t cfg = {};

@@ -103,7 +103,7 @@ struct vcb_engine {
     size_t h_stage_ints = 0;
     cudaEvent_t stage_ev = nullptr;
 
-    int opt_simt = 0, opt_pdl = 0, opt_profile = 0, opt_gemm_maxctas = 0, opt_gemm_stages = 0, opt_prefetch = 0;
+    int opt_simt = 0, opt_pdl = 0, opt_profile = 0, opt_gemm_maxctas = 0, opt_gemm_stages = 0, opt_prefetch = 0, opt_att_balance = 1;
     int64_t n_launches = 0;
     // profile mode: CUDA events around every launch, by kernel class
     struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -222,6 +222,7 @@ int run_gemm(vcb_engine* e, const Matrix& W, const CUtensorMap* tmB, const __nv_
     if (next && e->opt_prefetch) {
         g.pf_ptr = next->w;
         g.pf_bytes = packed_weight_elems(next->rows, next->cols) * 2;
+        if (e->opt_prefetch == 2) g.pf_bytes |= (1ull << 63);        // issue at the end of the weight stream
     }
     g.tmA = &W.tm;
     g.tmB = tmB;
@@ -265,7 +266,13 @@ int launch_attn_hd(vcb_engine* e, const Layer& Ly, int rows, int bpad, int max_c
     const int nch = std::min(e->att_maxch, std::max(1, (npages + e->att_chunk_pages - 1) / e->att_chunk_pages));
     const int n_rh = rows * m.H;
     const int per_sm = std::max(1, std::min(4, (227 * 1024) / (L::TOTAL + 1024)));
-    const int grid = std::min(n_rh * nch, e->num_sms * per_sm);
+    int grid = std::min(n_rh * nch, e->num_sms * per_sm);
+    if (e->opt_att_balance) {
+        // equal item counts per CTA: 512 items on 296 CTAs would leave 80 CTAs idle for the whole second pass and the
+        // kernel finishing at the pace of the 2-item CTAs; 256 CTAs x 2 items keep every stream alive until the end
+        const int items = n_rh * nch, passes = (items + grid - 1) / grid;
+        grid = (items + passes - 1) / passes;
+    }
     ProfScope ps(e, PC_ATTN, st);
     VCB_CUDA_OK(launch_k(e, attn_rows_kernel<KVT, HD>, dim3(grid), dim3(ATT_THREADS + 32), L::TOTAL, st, e->qbuf,
                          static_cast<const KVT*>(Ly.kpool), static_cast<const KVT*>(Ly.vpool), e->page_table,
@@ -687,6 +694,7 @@ int vcb_create(const vcb_config* cfg, vcb_engine** out) {
     if (getenv("VCB_GEMM_MAXCTAS")) e->opt_gemm_maxctas = atoi(getenv("VCB_GEMM_MAXCTAS"));
     if (getenv("VCB_GEMM_STAGES")) e->opt_gemm_stages = atoi(getenv("VCB_GEMM_STAGES"));
     if (getenv("VCB_PREFETCH")) e->opt_prefetch = atoi(getenv("VCB_PREFETCH"));
+    if (getenv("VCB_ATT_BALANCE")) e->opt_att_balance = atoi(getenv("VCB_ATT_BALANCE"));
     if (getenv("VCB_FOLD")) e->opt_fold = atoi(getenv("VCB_FOLD"));
     if (getenv("VCB_CHAIN")) e->opt_chain = atoi(getenv("VCB_CHAIN"));
     const char* acp = getenv("VCB_ATT_CHUNK_PAGES");
@@ -1226,12 +1234,13 @@ int vcb_bench_gemm(int32_t N, int32_t Kd, int32_t B, int32_t splits, int32_t sta
 int vcb_timeline(int32_t enable, uint64_t* out_host, int32_t max_records, int32_t* n_out) {
     static unsigned long long* buf = nullptr;
     static unsigned int* cnt = nullptr;
-    if (enable == 1) {
+    if (enable == 1 || enable == 2) {        // 2: every CTA records its start / wait / end as well
         if (!buf) {
             VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&buf), 65536 * 2 * sizeof(unsigned long long)));
-            VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&cnt), sizeof(unsigned int)));
+            VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&cnt), 2 * sizeof(unsigned int)));
         }
-        VCB_CUDA_OK(cudaMemset(cnt, 0, sizeof(unsigned int)));
+        const unsigned int init[2] = {0u, enable == 2 ? 1u : 0u};
+        VCB_CUDA_OK(cudaMemcpy(cnt, init, sizeof(init), cudaMemcpyHostToDevice));
         VCB_CUDA_OK(cudaMemcpyToSymbol(g_tl_buf, &buf, sizeof(buf)));
         VCB_CUDA_OK(cudaMemcpyToSymbol(g_tl_cnt, &cnt, sizeof(cnt)));
         gemm_timeline_set(buf, cnt);

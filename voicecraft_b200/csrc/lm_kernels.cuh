@@ -233,10 +233,11 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
         }
         mbar_fence_init();
         tl_mark(0x300);
+        tl_mark_all(0x300);
     }
     __syncthreads();
     pdl_wait();
-    if (threadIdx.x == 0) tl_mark(0x310);
+    if (threadIdx.x == 0) { tl_mark(0x310); tl_mark_all(0x310); }
     const int n_items = n_rh * n_chunks;
 
     if (warp == ATT_CWARPS) {
@@ -395,7 +396,7 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
         }
         named_bar_sync(1, ATT_THREADS);                       // s_last / red[] reused by the next item
     }
-    if (threadIdx.x == 0) tl_mark(0x330);
+    if (threadIdx.x == 0) { tl_mark(0x330); tl_mark_all(0x330); }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -143,8 +143,8 @@ __device__ __forceinline__ void prefetch_l2_slice(const void* ptr, unsigned long
 
 // Optional device-side timeline (debug): CTA 0 of instrumented kernels appends (tag, globaltimer ns) records.
 // Each translation unit has its own copy of the pointer; the host sets them through vcb_timeline_set().
-static __device__ unsigned long long* g_tl_buf = nullptr;
-static __device__ unsigned int* g_tl_cnt = nullptr;
+static __constant__ unsigned long long* g_tl_buf = nullptr;   // constant bank: the disabled check costs no L2 round trip
+static __constant__ unsigned int* g_tl_cnt = nullptr;
 __device__ __forceinline__ void tl_mark(unsigned int tag) {
     if (g_tl_buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
         unsigned long long t;
@@ -152,6 +152,19 @@ __device__ __forceinline__ void tl_mark(unsigned int tag) {
         const unsigned int i = atomicAdd(g_tl_cnt, 1u);
         if (i < 65536u) {
             g_tl_buf[2 * i] = tag;
+            g_tl_buf[2 * i + 1] = t;
+        }
+    }
+}
+
+// Every CTA records (vcb_timeline(2, ...)): tag | 0x8000 | cta << 16 -- used to see launch skew and stragglers.
+__device__ __forceinline__ void tl_mark_all(unsigned int tag) {
+    if (g_tl_buf != nullptr && g_tl_cnt[1] != 0u) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned int i = atomicAdd(g_tl_cnt, 1u);
+        if (i < 65536u) {
+            g_tl_buf[2 * i] = tag | 0x8000u | ((blockIdx.x + gridDim.x * blockIdx.y) << 16);
             g_tl_buf[2 * i + 1] = t;
         }
     }
