@@ -92,7 +92,8 @@ __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 pos[u] = (u < nrows) ? ep.row_pos[row0 + u] : -1;
-                slot[u] = (u < nrows) ? ep.row_slot[row0 + u] : 0;
+                slot[u] = (u < nrows && !ep.row_page) ? ep.row_slot[row0 + u] : 0;
+                page[u] = (u < nrows && ep.row_page) ? ep.row_page[row0 + u] : 0;      // same batch of loads as pos
             }
             const int part = m / ep.d, cc = m - part * ep.d;
             if (part == 0) {
@@ -101,9 +102,11 @@ __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0
                     if (pos[u] >= 0) ep.qbuf[static_cast<size_t>(row0 + u) * ep.d + cc] = sum[u] + bias;
                 return;
             }
+            if (!ep.row_page) {         // (precomputed by step_prep / prefill otherwise: one L2 round trip instead of two)
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                page[u] = (pos[u] >= 0) ? ep.page_table[slot[u] * ep.max_pages + pos[u] / ep.page_size] : 0;
+                for (int u = 0; u < 4; ++u)
+                    page[u] = (pos[u] >= 0) ? ep.page_table[slot[u] * ep.max_pages + pos[u] / ep.page_size] : 0;
+            }
             const int h = cc / ep.hd, e = cc - h * ep.hd;
             void* pool = (part == 1) ? ep.kpool : ep.vpool;
 #pragma unroll

@@ -6,6 +6,7 @@
 #include "lm_kernels.cuh"
 
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -88,9 +89,10 @@ struct vcb_engine {
     __nv_bfloat16 *act_d = nullptr, *act_d2 = nullptr, *act_f = nullptr, *act_h = nullptr;
     CUtensorMap tm_act_d[4], tm_act_d2[4], tm_act_f[4], tm_act_h[4];   // bpad = 16, 32, 64, 128
     int *row_slot = nullptr, *row_pos = nullptr, *row_last = nullptr, *page_table = nullptr;   // decode-step rows
-    int *all_rows = nullptr;          // prefill row tables: 4 arrays of all_rows_cap ints (seq, pos, slot, last)
+    int *row_page = nullptr;          // KV page of every row's position (step_prep / prefill fill it)
+    int *all_rows = nullptr;          // prefill row tables: 5 arrays of all_rows_cap ints (seq, pos, slot, last, page)
     size_t all_rows_cap = 0;
-    const int *cur_slot = nullptr, *cur_pos = nullptr, *cur_last = nullptr;   // tables used by forward_rows
+    const int *cur_slot = nullptr, *cur_pos = nullptr, *cur_last = nullptr, *cur_page = nullptr;   // tables used by forward_rows
     int *d_slots = nullptr;
     std::vector<int> last_slots;      // host mirror of d_slots (skip re-upload when unchanged)
     int *tok_log = nullptr;
@@ -103,6 +105,7 @@ struct vcb_engine {
     size_t h_stage_ints = 0;
     cudaEvent_t stage_ev = nullptr;
 
+    std::vector<std::array<int, 3>> opt_splits;
     int opt_simt = 0, opt_pdl = 0, opt_profile = 0, opt_gemm_maxctas = 0, opt_gemm_stages = 0, opt_prefetch = 0, opt_att_balance = 1;
     int64_t n_launches = 0;
     // profile mode: CUDA events around every launch, by kernel class
@@ -234,6 +237,8 @@ int run_gemm(vcb_engine* e, const Matrix& W, const CUtensorMap* tmB, const __nv_
     g.ldx = ldx;
     g.bpad = bpad;
     g.splits = gemm_pick_splits(W.rows, kdim, e->num_sms);
+    for (const auto& o : e->opt_splits)          // experiment knob VCB_SPLITS="<N>x<K>:<S>,..."
+        if (o[0] == W.rows && o[1] == kdim) g.splits = o[2];
     // >= 64 rows: the per-CTA epilogue / DSMEM exchange grows with the rows, so half the cluster size wins
     // (scripts/bench_gemm.py at B = 64 / 128: QKV 22.4 -> 17.5 us, out 16.4 -> 10.9, FFN1 23.0 -> 18.0, FFN2 25.4 -> 19.7 at B = 64)
     if (bpad >= 64 && g.splits > 1) g.splits /= 2;
@@ -342,6 +347,7 @@ int forward_rows(vcb_engine* e, int rows, int max_ctx, bool fold, cudaStream_t s
         ep.page_table = e->page_table;
         ep.row_slot = e->cur_slot;
         ep.row_pos = e->cur_pos;
+        ep.row_page = e->cur_page;
         ep.kv_fp32 = e->kv_fp32;
         ep.max_pages = e->max_pages_per_slot;
         ep.page_size = KV_PAGE;
@@ -695,6 +701,14 @@ int vcb_create(const vcb_config* cfg, vcb_engine** out) {
     if (getenv("VCB_GEMM_STAGES")) e->opt_gemm_stages = atoi(getenv("VCB_GEMM_STAGES"));
     if (getenv("VCB_PREFETCH")) e->opt_prefetch = atoi(getenv("VCB_PREFETCH"));
     if (getenv("VCB_ATT_BALANCE")) e->opt_att_balance = atoi(getenv("VCB_ATT_BALANCE"));
+    if (const char* sp = getenv("VCB_SPLITS")) {
+        int n = 0, k = 0, sv = 0, used = 0;
+        while (sscanf(sp, "%dx%d:%d%n", &n, &k, &sv, &used) == 3) {
+            e->opt_splits.push_back({n, k, sv});
+            sp += used;
+            if (*sp == ',') ++sp;
+        }
+    }
     if (getenv("VCB_FOLD")) e->opt_fold = atoi(getenv("VCB_FOLD"));
     if (getenv("VCB_CHAIN")) e->opt_chain = atoi(getenv("VCB_CHAIN"));
     const char* acp = getenv("VCB_ATT_CHUNK_PAGES");
@@ -875,14 +889,14 @@ int vcb_finalize_weights(vcb_engine* e) {
         if (getenv("VCB_CHAIN_FORCE")) e->chain_clusters[0] = e->chain_clusters[1] = atoi(getenv("VCB_CHAIN_FORCE"));
         e->chain_cache[0].clear();
         e->chain_cache[1].clear();
-        if (dalloc(&e->row_slot, R) || dalloc(&e->row_pos, R) || dalloc(&e->row_last, R) ||
+        if (dalloc(&e->row_slot, R) || dalloc(&e->row_pos, R) || dalloc(&e->row_last, R) || dalloc(&e->row_page, R) ||
             dalloc(&e->d_slots, R) || dalloc(&e->page_table, static_cast<size_t>(S) * e->max_pages_per_slot) ||
             dalloc(&e->tok_log, static_cast<size_t>(S) * e->cfg.max_new_tokens * m.K) ||
             dalloc(&e->dbg_logits, static_cast<size_t>(R) * m.K * m.V) || dalloc(&e->st, S) || dalloc(&e->gr, S) ||
             dalloc(&e->d_seqs, S))
             return -1;
         e->all_rows_cap = static_cast<size_t>(S) * e->cfg.max_seq_len;
-        if (dalloc(&e->all_rows, 4 * e->all_rows_cap)) return -1;
+        if (dalloc(&e->all_rows, 5 * e->all_rows_cap)) return -1;
         e->h_stage_ints = 4096;
         VCB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_stage), e->h_stage_ints * sizeof(int)));
         VCB_CUDA_OK(cudaEventCreateWithFlags(&e->stage_ev, cudaEventDisableTiming));
@@ -910,7 +924,7 @@ int vcb_prefill(vcb_engine* e, const vcb_prompt* prompts, int32_t n, void* strea
     const ModelDims& m = e->m;
     // ---- open slots / groups, allocate KV pages, build the row list ------------------------------------
     std::vector<EmbedSeq> seqs;
-    std::vector<int> r_seq, r_pos, r_slot, r_last;
+    std::vector<int> r_seq, r_pos, r_slot, r_last, r_page;
     std::vector<SlotState> sst;
     std::vector<int> sst_slot;
     std::vector<GroupState> gst;
@@ -982,6 +996,7 @@ int vcb_prefill(vcb_engine* e, const vcb_prompt* prompts, int32_t n, void* strea
                 r_pos.push_back(t);
                 r_slot.push_back(slot);
                 r_last.push_back(t == total - 1 ? slot : -1);
+                r_page.push_back(e->slot_pages[slot][t / KV_PAGE]);
             }
         }
     }
@@ -1010,15 +1025,18 @@ int vcb_prefill(vcb_engine* e, const vcb_prompt* prompts, int32_t n, void* strea
     int* t_pos = t_seq + e->all_rows_cap;
     int* t_slot = t_pos + e->all_rows_cap;
     int* t_last = t_slot + e->all_rows_cap;
+    int* t_page = t_last + e->all_rows_cap;
     VCB_CUDA_OK(cudaMemcpy(t_seq, r_seq.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
     VCB_CUDA_OK(cudaMemcpy(t_pos, r_pos.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
     VCB_CUDA_OK(cudaMemcpy(t_slot, r_slot.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
     VCB_CUDA_OK(cudaMemcpy(t_last, r_last.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
+    VCB_CUDA_OK(cudaMemcpy(t_page, r_page.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
     for (size_t off = 0; off < total_rows; off += vcb_engine::MAX_ROWS) {
         const int rows = static_cast<int>(std::min<size_t>(vcb_engine::MAX_ROWS, total_rows - off));
         e->cur_slot = t_slot + off;
         e->cur_pos = t_pos + off;
         e->cur_last = t_last + off;
+        e->cur_page = t_page + off;
         embed_rows_kernel<<<rows, 256, 0, st>>>(e->d_seqs, t_seq + off, t_pos + off, e->x_rows, m.d, m.K, e->E_text,
                                                 e->d_E_audio, e->mask_emb, e->pe, e->alpha_t, e->alpha_a);
         VCB_CUDA_OK(cudaGetLastError());
@@ -1063,12 +1081,13 @@ int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float*
         VCB_CUDA_OK(launch_k(e, step_prep_kernel, dim3(n), dim3(256), 0, st, e->d_slots, n, e->st, e->gr, e->row_slot,
                              e->row_pos, e->row_last, e->x_slot, e->x_rows, e->m.d,
                              fold ? e->layers[0].ln1_g : static_cast<const float*>(nullptr), e->act_d, bpad_for(n),
-                             e->ln_stats));
+                             e->ln_stats, e->page_table, e->max_pages_per_slot, e->row_page));
     }
     LAUNCH_COUNT(e);
     e->cur_slot = e->row_slot;
     e->cur_pos = e->row_pos;
     e->cur_last = e->row_last;
+    e->cur_page = e->row_page;
     int max_ctx = 1;
     for (int i = 0; i < n; ++i) max_ctx = std::max(max_ctx, ++e->h_seq_len[slots[i]]);
     if (fold && chain_usable(e, bpad_for(n))) {

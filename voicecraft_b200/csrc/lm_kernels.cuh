@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(256)
 step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ st, const GroupState* __restrict__ gr,
                  int* __restrict__ row_slot, int* __restrict__ row_pos, int* __restrict__ row_last,
                  const float* __restrict__ x_slot, float* __restrict__ x_rows, int d,
-                 const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats) {
+                 const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats,
+                 const int* __restrict__ page_table, int max_pages, int* __restrict__ row_page) {
     __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
@@ -421,6 +422,7 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
         row_slot[r] = slot;
         row_pos[r] = s_pos;
         row_last[r] = on ? slot : -1;
+        row_page[r] = on ? page_table[slot * max_pages + s_pos / KV_PAGE] : 0;
         if (on) {
             S.seq_len += 1;
             S.y_len += 1;

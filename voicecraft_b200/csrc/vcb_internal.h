@@ -24,6 +24,7 @@ struct GemmEpilogue {
     const int* page_table = nullptr;
     const int* row_slot = nullptr;
     const int* row_pos = nullptr;
+    const int* row_page = nullptr;      // optional: page index of (row_slot, row_pos), saves the dependent page-table lookup
     int kv_fp32 = 0, max_pages = 0, page_size = 64, d = 0, H = 0, hd = 0;
     // EPI_RESID: x[row, m] += y ; EPI_ACT: act hi/lo rows ; EPI_LOGITS: out[row, col_off + m]
     float* x = nullptr;
