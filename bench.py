@@ -281,15 +281,19 @@ def main():
                 bytes_per_launch = B * (S_prof + 1) * 2 * cfg.d_model * kvb      # K+V rows of every cached token, one layer
             else:
                 bytes_per_launch = Wb / (cnt[0] / nprof)                          # mean weight bytes per GEMM launch
-            dur = msb[dom] / cnt[dom] * 1e-3
+            # Average launch duration over the TIMED region: the kernel's share of the step (from the event-per-launch
+            # pass, which serialises launches and adds event overhead to each, so only the share is used) applied to
+            # the measured step time.  The isolated per-launch event time is reported next to it.
+            iso = msb[dom] / cnt[dom] * 1e-3
+            dur = (msb[dom] / total) * (ms / Ksteps * 1e-3) / (cnt[dom] / nprof)
             ach = bytes_per_launch / dur / 1e9
             # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_summary.md): the GEMMs
             # move exactly their weight bytes, attention 1.09x its algorithmic KV bytes
             traffic = bytes_per_launch * (1.09 if dom == 1 else 1.0)
             roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r01_ncu_summary.md (dram__bytes_read+write per launch / algorithmic)", "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": dur * 1e6,
+                    "traffic": traffic, "traffic_source": "profiles/r01_ncu_summary_v5.md (dram__bytes_read+write per launch / algorithmic)", "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": dur * 1e6, "isolated_launch_us": iso * 1e6,
                     "peak_source": peak_src, "ctx": S_prof, "by_kernel": shares,
-                    "note": "per-launch CUDA events serialise launches; shares, not absolutes, compare with ncu"}
+                    "note": "avg_launch_us = share of the step (event-per-launch pass) x timed step / launches; isolated_launch_us = raw per-launch event time (serialised, no PDL overlap)"}
     sess.close()
 
     # ------------------------------------------------------------------ e2e: public API, host in / host out
