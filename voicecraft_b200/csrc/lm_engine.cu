@@ -90,6 +90,8 @@ struct vcb_engine {
     CUtensorMap tm_act_d[4], tm_act_d2[4], tm_act_f[4], tm_act_h[4];   // bpad = 16, 32, 64, 128
     int *row_slot = nullptr, *row_pos = nullptr, *row_last = nullptr, *page_table = nullptr;   // decode-step rows
     int *row_page = nullptr;          // KV page of every row's position (step_prep / prefill fill it)
+    int *row_pages = nullptr;         // decode steps: per-row copy of the slot's page list [rows][max_pages_per_slot]
+    const int *cur_pages = nullptr;   // = row_pages during decode steps, null during prefill
     int *all_rows = nullptr;          // prefill row tables: 5 arrays of all_rows_cap ints (seq, pos, slot, last, page)
     size_t all_rows_cap = 0;
     const int *cur_slot = nullptr, *cur_pos = nullptr, *cur_last = nullptr, *cur_page = nullptr;   // tables used by forward_rows
@@ -282,7 +284,7 @@ int launch_attn_hd(vcb_engine* e, const Layer& Ly, int rows, int bpad, int max_c
     VCB_CUDA_OK(launch_k(e, attn_rows_kernel<KVT, HD>, dim3(grid), dim3(ATT_THREADS + 32), L::TOTAL, st, e->qbuf,
                          static_cast<const KVT*>(Ly.kpool), static_cast<const KVT*>(Ly.vpool), e->page_table,
                          e->max_pages_per_slot, e->cur_slot, e->cur_pos, m.H, e->act_d, m.d, bpad, scale, e->att_ws,
-                         e->att_cnt, e->att_maxch, e->att_chunk_pages, n_rh, nch));
+                         e->att_cnt, e->att_maxch, e->att_chunk_pages, n_rh, nch, e->cur_pages));
     LAUNCH_COUNT(e);
     return 0;
 }
@@ -728,7 +730,7 @@ int vcb_destroy(vcb_engine* e) {
     cudaFree(e->h1.w);
     for (auto& M : e->h2) cudaFree(M.w);
     void* ptrs[] = {e->b_h1, e->d_h2_maps, e->d_bias2, e->d_E_audio, e->pe, e->x_rows, e->qbuf, e->logits, e->att_ws, e->att_cnt, e->ln_stats, e->chain_ctr, e->x_slot, e->h_slot,
-                    e->act_d, e->act_d2, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->all_rows, e->page_table,
+                    e->act_d, e->act_d2, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->row_page, e->row_pages, e->all_rows, e->page_table,
                     e->d_slots, e->tok_log, e->dbg_logits, e->st, e->gr, e->d_seqs};
     for (void* p : ptrs) cudaFree(p);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -889,7 +891,7 @@ int vcb_finalize_weights(vcb_engine* e) {
         if (getenv("VCB_CHAIN_FORCE")) e->chain_clusters[0] = e->chain_clusters[1] = atoi(getenv("VCB_CHAIN_FORCE"));
         e->chain_cache[0].clear();
         e->chain_cache[1].clear();
-        if (dalloc(&e->row_slot, R) || dalloc(&e->row_pos, R) || dalloc(&e->row_last, R) || dalloc(&e->row_page, R) ||
+        if (dalloc(&e->row_slot, R) || dalloc(&e->row_pos, R) || dalloc(&e->row_last, R) || dalloc(&e->row_page, R) || dalloc(&e->row_pages, static_cast<size_t>(R) * e->max_pages_per_slot) ||
             dalloc(&e->d_slots, R) || dalloc(&e->page_table, static_cast<size_t>(S) * e->max_pages_per_slot) ||
             dalloc(&e->tok_log, static_cast<size_t>(S) * e->cfg.max_new_tokens * m.K) ||
             dalloc(&e->dbg_logits, static_cast<size_t>(R) * m.K * m.V) || dalloc(&e->st, S) || dalloc(&e->gr, S) ||
@@ -1037,6 +1039,7 @@ int vcb_prefill(vcb_engine* e, const vcb_prompt* prompts, int32_t n, void* strea
         e->cur_pos = t_pos + off;
         e->cur_last = t_last + off;
         e->cur_page = t_page + off;
+        e->cur_pages = nullptr;
         embed_rows_kernel<<<rows, 256, 0, st>>>(e->d_seqs, t_seq + off, t_pos + off, e->x_rows, m.d, m.K, e->E_text,
                                                 e->d_E_audio, e->mask_emb, e->pe, e->alpha_t, e->alpha_a);
         VCB_CUDA_OK(cudaGetLastError());
@@ -1081,13 +1084,14 @@ int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float*
         VCB_CUDA_OK(launch_k(e, step_prep_kernel, dim3(n), dim3(256), 0, st, e->d_slots, n, e->st, e->gr, e->row_slot,
                              e->row_pos, e->row_last, e->x_slot, e->x_rows, e->m.d,
                              fold ? e->layers[0].ln1_g : static_cast<const float*>(nullptr), e->act_d, bpad_for(n),
-                             e->ln_stats, e->page_table, e->max_pages_per_slot, e->row_page));
+                             e->ln_stats, e->page_table, e->max_pages_per_slot, e->row_page, e->row_pages));
     }
     LAUNCH_COUNT(e);
     e->cur_slot = e->row_slot;
     e->cur_pos = e->row_pos;
     e->cur_last = e->row_last;
     e->cur_page = e->row_page;
+    e->cur_pages = e->row_pages;
     int max_ctx = 1;
     for (int i = 0; i < n; ++i) max_ctx = std::max(max_ctx, ++e->h_seq_len[slots[i]]);
     if (fold && chain_usable(e, bpad_for(n))) {

@@ -209,7 +209,7 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
                  const int* __restrict__ page_table, int max_pages, const int* __restrict__ row_slot,
                  const int* __restrict__ row_pos, int H, __nv_bfloat16* __restrict__ act, int ld_act, int bpad,
                  float scale, float* __restrict__ ws, int* __restrict__ cnt, int maxch, int chunk_pages, int n_rh,
-                 int n_chunks) {
+                 int n_chunks, const int* __restrict__ row_pages) {
     using L = AttSmem<KVT, HD>;
     constexpr int LPT = HD / 8;          // lanes per key in QK
     constexpr int TPW = 32 / LPT;        // keys per warp iteration
@@ -254,7 +254,9 @@ attn_rows_kernel(const float* __restrict__ qbuf, const KVT* __restrict__ kpool, 
                 const int p0 = chunk * chunk_pages;
                 if (p0 >= npages) continue;
                 const int p1 = min(npages, p0 + chunk_pages);
-                const int* pt = page_table + row_slot[r] * max_pages;
+                // decode steps: step_prep left a per-row copy of the slot's page list, so the first TMA issue is one
+                // L2 round trip away (row -> pages) instead of two (row -> slot -> pages)
+                const int* pt = row_pages ? row_pages + r * max_pages : page_table + row_slot[r] * max_pages;
                 for (int p = p0; p < p1; ++p, ++it) {
                     const int s = it % ATT_STAGES;
                     if (it >= ATT_STAGES) mbar_wait(&empty[s], ((it / ATT_STAGES) - 1) & 1);
@@ -408,7 +410,8 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
                  int* __restrict__ row_slot, int* __restrict__ row_pos, int* __restrict__ row_last,
                  const float* __restrict__ x_slot, float* __restrict__ x_rows, int d,
                  const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats,
-                 const int* __restrict__ page_table, int max_pages, int* __restrict__ row_page) {
+                 const int* __restrict__ page_table, int max_pages, int* __restrict__ row_page,
+                 int* __restrict__ row_pages) {
     __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
@@ -428,6 +431,8 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
             S.y_len += 1;
         }
     }
+    for (int j = threadIdx.x; j < max_pages; j += blockDim.x)       // the attention producer reads these by row
+        row_pages[static_cast<size_t>(r) * max_pages + j] = page_table[slot * max_pages + j];
     __syncthreads();
     if (s_pos < 0) return;
     // x row + (LayerNorm folding) gamma0 * x as hi/lo rows and the row statistics for layer 0's QKV GEMM
@@ -582,6 +587,14 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
         l[j] = u;
     }
 
+    // the Exp(1) draws are independent of everything below: fetch them now, not after the softmax
+    float nz[SAMP_MAXV];
+#pragma unroll
+    for (int j = 0; j < SAMP_MAXV; ++j) {
+        const int v = tid + j * SAMP_THREADS;
+        nz[j] = (v < V) ? a.noise[static_cast<size_t>(row) * V + v] : 1.f;
+    }
+
     // ---- argmax of the edited logits (first index wins), needed for the end-token trigger ----------
     float bm = -INFINITY;
     int bi = 0x7fffffff;
@@ -628,9 +641,15 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
 #pragma unroll
             for (int j = 0; j < SAMP_MAXV; ++j) {
                 const int v = tid + j * SAMP_THREADS;
-                if (v < V) {
-                    const uint32_t key = f2key(l[j]);
-                    if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1);
+                // warp-aggregated histogram update: logits share a handful of exponent bytes, so plain atomics would
+                // serialise ~32-way on the same shared-memory word in the first passes
+                const uint32_t key = v < V ? f2key(l[j]) : 0u;
+                const bool in = v < V && (key & pmask) == prefix;
+                const unsigned act = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int bin = (key >> shift) & 0xff;
+                    const unsigned peers = __match_any_sync(act, bin);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
                 }
             }
             __syncthreads();
@@ -775,7 +794,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
         const int v = tid + j * SAMP_THREADS;
         if (v < V) {
             const float p = ev[j] / tot;
-            const float sc = p / a.noise[static_cast<size_t>(row) * V + v];
+            const float sc = p / nz[j];
             if (sc > best || (sc == best && v < besti)) { best = sc; besti = v; }
         }
     }

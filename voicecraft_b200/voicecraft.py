@@ -18,6 +18,7 @@ Out of scope (training): ``forward`` and ``prepare_mask_intervals`` raise NotImp
 import copy
 import ctypes as C
 import logging
+import os
 from argparse import Namespace
 from typing import Dict, List, Optional
 
@@ -97,6 +98,44 @@ class _Decoder(nn.Module):
         self.norm = nn.LayerNorm(d, eps=1e-5)
 
 
+class _NoiseRing:
+    """Exp(1) draws for the fused sampler, generated on a side stream.
+
+    The draw for step i does not depend on step i-1, but as a kernel on the decode stream it sits between the sampler of
+    step i-1 and the first kernel of step i (two grid drains + ~5 us every step).  Here the same ``exponential_`` calls
+    are issued in the same host order (the generator state advances exactly as before) on a second stream into a small
+    ring of buffers; events order producer -> consumer (ready) and consumer -> producer (buffer reuse)."""
+
+    def __init__(self, shape, device, depth=4):
+        self.bufs = [torch.empty(shape, device=device, dtype=torch.float32) for _ in range(depth)]
+        self.side = torch.cuda.Stream(device=device)
+        for b in self.bufs:
+            b.record_stream(self.side)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.freed = [None] * depth
+        self.i = 0
+        # the buffers were allocated on the current stream
+        self.side.wait_stream(torch.cuda.current_stream(device))
+
+    def draw(self):
+        """enqueue one draw; returns (buffer, token): the current stream waits for it, call consumed(token) after the
+        launch that reads it"""
+        j = self.i % len(self.bufs)
+        self.i += 1
+        if self.freed[j] is not None:
+            self.side.wait_event(self.freed[j])
+        with torch.cuda.stream(self.side):
+            self.bufs[j].exponential_(1)
+            self.ready[j].record(self.side)
+        torch.cuda.current_stream(self.bufs[j].device).wait_event(self.ready[j])
+        return self.bufs[j], j
+
+    def consumed(self, j):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.bufs[j].device))
+        self.freed[j] = ev
+
+
 class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
     def __new__(cls, args: Optional[Namespace] = None, config: Optional[Dict] = None, **kwargs):
         if args is not None:
@@ -150,6 +189,7 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         self._eng_key = None
         self._eng_opts = dict(max_slots=8, max_seq_len=2048, max_new_tokens=4096, kv_dtype="bf16")
         self.noise_fn = None          # optional: callable(shape, device) -> fp32 Exp(1) tensor on `device`
+        self.side_stream_noise = os.environ.get("VCB_SIDE_NOISE", "1") != "0"
         self.poll_every = 4           # inference_tts*: poll the done flag every N steps (device generator only)
         self.last_stats = {}
         self.trace_logits = None      # set to a list to collect the raw logits [n*K, V] of every sampling step
@@ -250,6 +290,18 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             sp.silence_tokens[i] = int(t)
         return sp
 
+    def _noise_source(self, shape, device):
+        """returns draw() -> (tensor, done_callback): device-generator draws come from a side-stream ring, custom
+        ``noise_fn`` draws from one persistent buffer on the decode stream"""
+        if self.noise_fn is None and self.side_stream_noise:
+            ring = _NoiseRing(shape, device)
+            def draw():
+                buf, tok = ring.draw()
+                return buf, (lambda: ring.consumed(tok))
+            return draw
+        buf = torch.empty(shape, device=device, dtype=torch.float32)
+        return lambda: (self._draw_noise(buf), (lambda: None))
+
     def _draw_noise(self, buf):
         """Exp(1) noise with the call shape of the reference's multinomial draw (in place on a persistent buffer)."""
         if self.noise_fn is not None:
@@ -282,7 +334,7 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         K, V = a.n_codebooks, self.n_audio_tokens[0]
         n = len(slots)
         c_slots = (C.c_int32 * n)(*slots)
-        noise = torch.empty(n_rows * K, V, device=dev, dtype=torch.float32)
+        draw = self._noise_source((n_rows * K, V), dev)
         status = (_lib.vcb_status * n)()
         def trace():
             if self.trace_logits is not None:
@@ -292,9 +344,10 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         every = max(1, int(self.poll_every)) if (speculative and self.noise_fn is None and self.trace_logits is None) else 1
         gen = torch.cuda.default_generators[dev.index or 0] if every > 1 else None
         off0 = gen.get_offset() if gen is not None else 0
-        self._draw_noise(noise)
+        noise, used_up = draw()
         delta = (gen.get_offset() - off0) if gen is not None else 0      # generator advance per draw of this shape
         _lib.check(lib.vcb_sample(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
+        used_up()
         trace()
         steps = 1
         while True:
@@ -309,9 +362,10 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
                 break
             forced = every == 1 and any(s.forced for s in status)
             if not forced:                               # forced hand-over steps consume no random numbers
-                self._draw_noise(noise)
+                noise, used_up = draw()
             _lib.check(lib.vcb_decode_step(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
             if not forced:
+                used_up()
                 trace()
             steps += 1
         if gen is not None and delta > 0:
@@ -606,7 +660,7 @@ class DecodeSession:
                 P[i].more_mask_rows[j] = int(v)
         self.c_slots = (C.c_int32 * self.B)(*range(self.B))
         self.status = (_lib.vcb_status * self.B)()
-        self.noise = torch.empty(self.B * K, self.V, device=dev, dtype=torch.float32)
+        self._draw = model._noise_source((self.B * K, self.V), dev)
         self.steps = 0
         self._open = True
         with torch.cuda.device(dev):
@@ -616,15 +670,17 @@ class DecodeSession:
 
     def sample(self):
         """first sampling step (on the prefill's last hidden states)"""
-        self.model._draw_noise(self.noise)
-        _lib.check(self.lib.vcb_sample(self.eng, self.c_slots, self.B, self.noise.data_ptr(), C.byref(self.sp), self.stream))
+        noise, used_up = self._draw()
+        _lib.check(self.lib.vcb_sample(self.eng, self.c_slots, self.B, noise.data_ptr(), C.byref(self.sp), self.stream))
+        used_up()
         self.steps += 1
 
     def step(self):
         # edit sessions: forced hand-over steps of individual utterances simply ignore their noise rows
-        self.model._draw_noise(self.noise)
-        _lib.check(self.lib.vcb_decode_step(self.eng, self.c_slots, self.B, self.noise.data_ptr(), C.byref(self.sp),
+        noise, used_up = self._draw()
+        _lib.check(self.lib.vcb_decode_step(self.eng, self.c_slots, self.B, noise.data_ptr(), C.byref(self.sp),
                                             self.stream))
+        used_up()
         self.steps += 1
 
     def poll(self):
