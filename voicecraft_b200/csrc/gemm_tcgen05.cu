@@ -31,7 +31,10 @@ namespace vcb {
 
 static constexpr int GEMM_BM = 128;   // output features per CTA (UMMA M)
 static constexpr int GEMM_BK = 64;    // K elements per pipeline stage (= 128 B of bf16 = one swizzle row)
-static constexpr int GEMM_THREADS = 192;
+// threads per CTA: w0 TMA, w1 MMA, then 4 epilogue warps (one per TMEM lane quarter); tiles with >= 64 token rows get a
+// second set of 4 that takes the other half of the rows (the epilogue, not the weight stream, dominates those launches)
+constexpr int gemm_epi_warps(int bn) { return bn >= 128 ? 8 : 4; }
+constexpr int gemm_threads(int bn) { return 64 + 32 * gemm_epi_warps(bn); }
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -152,12 +155,14 @@ __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(gemm_threads(BN))
 gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmEpilogue ep, int Nout, int total_kb, int kb_per_split, int b_col_off, int nvalid,
                   const void* pf_ptr, unsigned long long pf_bytes, const GemmGroup grp) {
     using L = GemmSmem<BN, STAGES>;
     constexpr int BPAD = BN / 2;
+    constexpr int HALVES = gemm_epi_warps(BN) / 4;          // epilogue warp sets, each covering all 128 TMEM lanes
+    constexpr int EPI_THREADS = 32 * gemm_epi_warps(BN);
     extern __shared__ __align__(1024) uint8_t smem[];       // SWIZZLE_128B tiles need 1024-byte alignment
     float* red = reinterpret_cast<float*>(smem + L::RED_OFFSET);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -271,6 +276,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ===== epilogue part 1: TMEM -> registers -> reduce-scatter over the cluster (DSMEM) =========
         const int q = warp & 3;                             // TMEM lane quarter owned by this warp
+        const int half = (warp - 2) >> 2;                   // which set of 4 epilogue warps (0 unless HALVES == 2)
         const int ml = q * 32 + lane;                       // feature inside the tile
         const int R = BPAD / S;                             // token rows owned by each CTA (power of two)
         const int shR = 31 - __clz(R);
@@ -286,7 +292,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // red layout in the owner: [writer z][feature ml][R rows] -- a thread's R partials for one owner are contiguous
         // (16-byte vector stores when R >= 4).  All Bpad rows are sent, valid or not: the byte count is a constant.
 #pragma unroll 1
-        for (int c = 0; c < BPAD; c += CH) {
+        for (int c = half * (BPAD / HALVES); c < (half + 1) * (BPAD / HALVES); c += CH) {
             float hi[CH], lo[CH];
             if (nkb > 0) {
                 if constexpr (CH == 32) {
@@ -329,16 +335,19 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // peers only ever write into `red`.  (Static __shared__ here would cost the second resident CTA per SM.)
         float* s_mean = reinterpret_cast<float*>(smem);
         float* s_rstd = s_mean + GEMM_BM;
-        float (*s_part)[4][2] = reinterpret_cast<float (*)[4][2]>(s_rstd + GEMM_BM);
+        float (*s_part_all)[4][4][2] = reinterpret_cast<float (*)[4][4][2]>(s_rstd + GEMM_BM);
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float (*s_part)[4][2] = s_part_all[half];
         const int ml = q * 32 + lane;
+        const int et = static_cast<int>(threadIdx.x) - 64;  // index among the epilogue threads
         const int m = m0 + ml;
         const int R = BPAD / S;
         const bool valid_m = m < Nout;
         pdl_wait();                                         // x / stats of earlier kernels are read below
         if (ep.ln_fold) {
             // mean / rstd of my rows from the per-tile partial sums the producer kernel left (fixed tile order)
-            for (int rr = ml; rr < R; rr += GEMM_BM) {
+            for (int rr = et; rr < R; rr += EPI_THREADS) {
                 const int row = z * R + rr;
                 float mean = 0.f, rstd = 0.f;
                 if (row < nvalid) {
@@ -363,10 +372,12 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 s_mean[rr] = mean;
                 s_rstd[rr] = rstd;
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 4, %0;" ::"n"(EPI_THREADS) : "memory");
         }
         const float bias = w_bias, cv = w_cv, gnext = w_gnext;
-        for (int rr0 = 0; rr0 < R; rr0 += 4) {
+        // the two warp sets (if any) alternate over the groups of 4 rows; each has its own named barrier (2 + half),
+        // so they may run a different number of groups
+        for (int rr0 = 4 * half; rr0 < R; rr0 += 4 * HALVES) {
             const int row0 = z * R + rr0;
             const int nrows = min(min(4, R - rr0), nvalid - row0);
             if (nrows <= 0) break;
@@ -403,14 +414,16 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         s_part[q][u][1] = p2[u];
                     }
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                else asm volatile("bar.sync 3, 128;" ::: "memory");
                 if (ml < 8) {
                     const int u = ml >> 1, w = ml & 1;
                     if (u < nrows)
                         ep.stats_out[(static_cast<size_t>(mt) * STATS_ROWS + row0 + u) * 2 + w] =
                             s_part[0][u][w] + s_part[1][u][w] + s_part[2][u][w] + s_part[3][u][w];
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+                else asm volatile("bar.sync 3, 128;" ::: "memory");
             }
         }
         if (threadIdx.x == 64) tl_mark(0x160 + ep.mode);
@@ -591,14 +604,14 @@ static int launch_one(const GemmCall& g, cudaStream_t st) {
         attr_set = true;
         if (getenv("VCB_DEBUG_OCC")) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_w_xT_cluster<BN, STAGES>, GEMM_THREADS, L::TOTAL);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_w_xT_cluster<BN, STAGES>, gemm_threads(BN), L::TOTAL);
             fprintf(stderr, "[vcb] gemm<%d,%d>: %d B smem, %d CTAs/SM (occupancy API)\n", BN, STAGES, L::TOTAL, nb);
         }
     }
     const int tiles = (g.Nout + GEMM_BM - 1) / GEMM_BM;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles * g.splits, g.grp.tmA ? g.groups : 1, 1);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(BN));
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
