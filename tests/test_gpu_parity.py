@@ -166,3 +166,49 @@ def test_capacity_exhaustion_is_reported():
     x, xl, y = synthetic.synthetic_utterance(cfg, 9, text_len=8, prompt_frames=10)
     with pytest.raises(_lib.VcbError):
         m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), top_k=10)
+
+
+def test_full_size_830M_first_steps_match_oracle():
+    """BASELINE.json configs[1] at full size (giga830M: d=2048, 16 layers, 16 heads, K=4): prefill + the first sampling
+    steps of one utterance, CUDA path (fp32 KV) vs the CPU oracle on the same synthetic checkpoint and the same Exp(1)
+    noise.  Token ids identical, raw logits within LOGIT_TOL.  (Long generations at this size are covered by the
+    size-independent checks: batched == single, generator stream, and scripts/parity_rate.py.)"""
+    from oracle import lm_oracle
+    from voicecraft_b200 import synthetic
+    n_steps = 24
+    cfg = synthetic.make_config("830M")
+    sd = synthetic.make_state_dict(cfg, seed=3)
+    x, x_lens, y = synthetic.synthetic_utterance(cfg, 4242, 16, 24)
+    kw = dict(top_k=40, top_p=1.0, temperature=1.0, stop_repetition=3, silence_tokens=gu.SILENCE)
+    torch.set_num_threads(max(1, min(16, torch.get_num_threads())))
+    oracle = lm_oracle.OracleLM(cfg, sd)
+    ref_rows = oracle.inference_tts(x, x_lens, y, noise_fn=gu.cpu_noise_fn(11), max_steps=n_steps, trace_logits=True, **kw)
+    assert ref_rows.shape == (n_steps, cfg.n_codebooks), "the synthetic checkpoint must not end within the first steps"
+    ref_trace = [t.numpy() for t in oracle.logit_trace]
+    del oracle
+
+    m = _model(cfg, sd, kv="fp32")
+    m.noise_fn = gu.cpu_noise_fn(11)
+    sess = m.open_tts_session([x.cuda()], [y.cuda()], **kw)
+    try:
+        sess.sample()
+        t = torch.empty(cfg.n_codebooks, m.n_audio_tokens[0], device="cuda")
+        lib = sess.lib
+        traces = []
+        def grab():
+            from voicecraft_b200 import _lib
+            _lib.check(lib.vcb_debug_logits(sess.eng, t.data_ptr(), cfg.n_codebooks))
+            traces.append(t.cpu().numpy().copy())
+        grab()
+        for _ in range(n_steps - 1):
+            sess.step()
+            grab()
+        rows = sess.raw_tokens(0)
+    finally:
+        sess.close()
+    worst = 0.0
+    for got, ref in zip(traces, ref_trace):
+        live = ref > -9999
+        worst = max(worst, float(np.abs(got - ref)[live].max()))
+    assert worst <= LOGIT_TOL, f"max |logit - oracle| = {worst}"
+    assert np.array_equal(rows[:n_steps], ref_rows.numpy()), "token ids differ from the oracle at full size"
