@@ -105,6 +105,9 @@ int vcb_release(vcb_engine* e, int32_t slot, int32_t n_copies);
 int vcb_debug_logits(vcb_engine* e, float* out_dev, int32_t n_rows);   /* last sampled logits [n*K][V] (pre-edit) */
 int vcb_debug_gemm(const float* W_dev /*[N][K]*/, const float* X_dev /*[B][K]*/, float* out_dev /*[B][N]*/, int32_t N,
                    int32_t K, int32_t B, int32_t splits /*<=0: auto*/, int32_t simt);
+/* same check for the rows-as-M prefill GEMM (csrc/gemm_rows.cu): any number of rows, N % 128 == 0, K % 64 == 0 */
+int vcb_debug_gemm_rows(const float* W_dev /*[N][K]*/, const float* X_dev /*[rows][K]*/, float* out_dev /*[rows][N]*/,
+                        int32_t N, int32_t K, int32_t rows);
 /* debug timeline: enable=1 starts recording (tag, globaltimer ns) pairs from CTA 0 of each kernel; enable=0 stops and
  * copies up to max_records pairs to out_host */
 int vcb_timeline(int32_t enable, uint64_t* out_host, int32_t max_records, int32_t* n_out);

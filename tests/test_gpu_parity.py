@@ -212,3 +212,34 @@ def test_full_size_830M_first_steps_match_oracle():
         worst = max(worst, float(np.abs(got - ref)[live].max()))
     assert worst <= LOGIT_TOL, f"max |logit - oracle| = {worst}"
     assert np.array_equal(rows[:n_steps], ref_rows.numpy()), "token ids differ from the oracle at full size"
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 40), (768, 256, 300), (1024, 4096, 1000), (6144, 2048, 513), (384, 512, 129)])
+def test_gemm_rows_vs_fp32(shape):
+    """Rows-as-M tcgen05 GEMM of the wide prefill path (csrc/gemm_rows.cu) against torch fp64: 256-wide tiles (even number
+    of 128-feature blocks), 128-wide tiles (odd: 384), ragged last row tile."""
+    from voicecraft_b200 import _lib
+    lib = _lib.load()
+    N, K, R = shape
+    g = torch.Generator(device="cpu").manual_seed(N + K + R)
+    W = torch.randn(N, K, generator=g).to(torch.bfloat16).float().cuda()
+    X = torch.randn(R, K, generator=g).cuda()
+    out = torch.zeros(R, N, device="cuda")
+    _lib.check(lib.vcb_debug_gemm_rows(W.data_ptr(), X.data_ptr(), out.data_ptr(), N, K, R))
+    ref = (X.double() @ W.double().t()).float()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-4 * max(scale, 1.0), f"shape={shape} err={err} scale={scale}"
+
+
+@pytest.mark.parametrize("name", ["tts_topk40", "batch3", "edit2"])
+def test_wide_prefill_matches_reference_fixture(name, monkeypatch):
+    """VCB_PREFILL_WIDE=1: the whole prompt goes through the rows-as-M GEMM path; tokens must still equal the reference's."""
+    monkeypatch.setenv("VCB_PREFILL_WIDE", "1")
+    res, trace, g = _run_case(name, CASES[name], "fp32")
+    for step, ref in zip(g["trace_steps"], g["trace_logits"]):
+        got = trace[int(step)].cpu().numpy()
+        live = ref > -9999
+        diff = np.abs(got - ref)[live]
+        assert int((diff > LOGIT_TOL).sum()) <= 1, f"step {step}: max {diff.max()}"
+    assert np.array_equal(res.cpu().numpy(), g["res"]), "token ids differ from the reference fixture"

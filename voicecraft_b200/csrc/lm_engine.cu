@@ -109,6 +109,17 @@ struct vcb_engine {
 
     std::vector<std::array<int, 3>> opt_splits;
     int opt_simt = 0, opt_pdl = 0, opt_profile = 0, opt_gemm_maxctas = 0, opt_gemm_stages = 0, opt_prefetch = 0, opt_att_balance = 1;
+    // wide prefill (gemm_rows.cu): up to wide_rows prompt rows per pass through the layers, own activation planes;
+    // opt_prefill_wide = minimum number of prompt rows that takes this path (0: never; VCB_PREFILL_WIDE)
+    int opt_prefill_wide = 0, wide_rows = 0;
+    float *wx = nullptr, *wq = nullptr, *w_att_ws = nullptr;
+    int* w_att_cnt = nullptr;
+    __nv_bfloat16 *wact_d = nullptr, *wact_f = nullptr;
+    CUtensorMap tm_wact_d, tm_wact_f;
+    // buffers the attention / LayerNorm launchers work on (narrow decode buffers unless a wide prefill pass is running)
+    float *cur_q = nullptr, *cur_att_ws = nullptr;
+    int* cur_att_cnt = nullptr;
+    __nv_bfloat16* cur_act_d = nullptr;
     int64_t n_launches = 0;
     // profile mode: CUDA events around every launch, by kernel class
     struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -281,10 +292,12 @@ int launch_attn_hd(vcb_engine* e, const Layer& Ly, int rows, int bpad, int max_c
         grid = (items + passes - 1) / passes;
     }
     ProfScope ps(e, PC_ATTN, st);
-    VCB_CUDA_OK(launch_k(e, attn_rows_kernel<KVT, HD>, dim3(grid), dim3(ATT_THREADS + 32), L::TOTAL, st, e->qbuf,
+    VCB_CUDA_OK(launch_k(e, attn_rows_kernel<KVT, HD>, dim3(grid), dim3(ATT_THREADS + 32), L::TOTAL, st,
+                         static_cast<const float*>(e->cur_q ? e->cur_q : e->qbuf),
                          static_cast<const KVT*>(Ly.kpool), static_cast<const KVT*>(Ly.vpool), e->page_table,
-                         e->max_pages_per_slot, e->cur_slot, e->cur_pos, m.H, e->act_d, m.d, bpad, scale, e->att_ws,
-                         e->att_cnt, e->att_maxch, e->att_chunk_pages, n_rh, nch, e->cur_pages));
+                         e->max_pages_per_slot, e->cur_slot, e->cur_pos, m.H, e->cur_act_d ? e->cur_act_d : e->act_d, m.d, bpad,
+                         scale, e->cur_att_ws ? e->cur_att_ws : e->att_ws, e->cur_att_cnt ? e->cur_att_cnt : e->att_cnt,
+                         e->att_maxch, e->att_chunk_pages, n_rh, nch, e->cur_pages));
     LAUNCH_COUNT(e);
     return 0;
 }
@@ -301,10 +314,11 @@ int launch_ln(vcb_engine* e, const float* x_in, const int* src_index, int bpad, 
               cudaStream_t st) {
     const int d = e->m.d;
     ProfScope ps(e, PC_LN, st);
+    __nv_bfloat16* dst = e->cur_act_d ? e->cur_act_d : e->act_d;
     if (d <= 2048)
-        VCB_CUDA_OK(launch_k(e, ln_rows_kernel<8>, dim3(rows), dim3(256), 0, st, x_in, src_index, g, b, e->act_d, d, bpad, d, 1e-5f));
+        VCB_CUDA_OK(launch_k(e, ln_rows_kernel<8>, dim3(rows), dim3(256), 0, st, x_in, src_index, g, b, dst, d, bpad, d, 1e-5f));
     else
-        VCB_CUDA_OK(launch_k(e, ln_rows_kernel<16>, dim3(rows), dim3(256), 0, st, x_in, src_index, g, b, e->act_d, d, bpad, d, 1e-5f));
+        VCB_CUDA_OK(launch_k(e, ln_rows_kernel<16>, dim3(rows), dim3(256), 0, st, x_in, src_index, g, b, dst, d, bpad, d, 1e-5f));
     LAUNCH_COUNT(e);
     return 0;
 }
@@ -387,6 +401,99 @@ int forward_rows(vcb_engine* e, int rows, int max_ctx, bool fold, cudaStream_t s
         if (run_gemm(e, Ly.ff2, &e->tm_act_f[bi], e->act_f, m.F, bpad, rows, 0, m.F, e2, st,
                      l + 1 < m.L ? &e->layers[l + 1].qkv : &e->h1))
             return -1;
+    }
+    return 0;
+}
+
+// Prefill over many rows at once (gemm_rows.cu): same layer sequence as forward_rows(fold = false), but every GEMM sees
+// all `rows` (<= wide_rows) rows as its M dimension; activations live in the wide planes [2][wide_rows][.] (the lo
+// plane starts wide_rows rows after the hi plane, which is what the LN / attention kernels take as their `bpad`).
+bool wide_usable(const vcb_engine* e) {
+    const ModelDims& m = e->m;
+    return e->opt_prefill_wide && !e->opt_simt && m.hd % 32 == 0 && gemm_rows_supported(3 * m.d, m.d, m.hd) &&
+           gemm_rows_supported(m.F, m.d, 0) && gemm_rows_supported(m.d, m.F, 0) && (m.hd == 128 || m.hd == 64);
+}
+
+int wide_alloc(vcb_engine* e) {
+    if (e->wx) return 0;
+    const ModelDims& m = e->m;
+    const size_t W = static_cast<size_t>(e->wide_rows);
+    auto dalloc = [&](auto** p, size_t n) -> int {
+        if (cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(**p)) != cudaSuccess) {
+            set_error("wide prefill: out of device memory (%zu elements)", n);
+            return 1;
+        }
+        return cudaMemset(*p, 0, n * sizeof(**p)) != cudaSuccess ? 1 : 0;
+    };
+    if (dalloc(&e->wx, W * m.d) || dalloc(&e->wq, W * m.d) || dalloc(&e->wact_d, 2 * W * m.d) ||
+        dalloc(&e->wact_f, 2 * W * m.F) || dalloc(&e->w_att_ws, W * m.H * e->att_maxch * (m.hd + 2)) ||
+        dalloc(&e->w_att_cnt, W * m.H))
+        return -1;
+    if (make_tmap_bf16_2d(&e->tm_wact_d, e->wact_d, 2 * W, m.d, m.d, 128) ||
+        make_tmap_bf16_2d(&e->tm_wact_f, e->wact_f, 2 * W, m.F, m.F, 128))
+        return -1;
+    return 0;
+}
+
+int forward_rows_wide(vcb_engine* e, int rows, int max_ctx, cudaStream_t st) {
+    const ModelDims& m = e->m;
+    const int W = e->wide_rows;
+    auto gemm = [&](const Matrix& Wt, const CUtensorMap* tmX, int kdim, const GemmEpilogue& ep) {
+        RowsGemmCall g;
+        g.tmX = tmX;
+        g.tmW = &Wt.tm;
+        g.ep = ep;
+        g.rows = rows;
+        g.rcap = W;
+        g.Nout = Wt.rows;
+        g.Kdim = kdim;
+        g.pdl = e->opt_pdl;
+        LAUNCH_COUNT(e);
+        ProfScope ps(e, PC_GEMM, st);
+        return gemm_rows_launch(g, st);
+    };
+    for (int l = 0; l < m.L; ++l) {
+        const Layer& Ly = e->layers[l];
+        if (launch_ln(e, e->wx, nullptr, W, Ly.ln1_g, Ly.ln1_b, rows, st)) return -1;
+        GemmEpilogue ep;
+        ep.mode = EPI_QKV;
+        ep.bias = Ly.b_qkv;
+        ep.qbuf = e->wq;
+        ep.kpool = Ly.kpool;
+        ep.vpool = Ly.vpool;
+        ep.page_table = e->page_table;
+        ep.row_slot = e->cur_slot;
+        ep.row_pos = e->cur_pos;
+        ep.row_page = e->cur_page;
+        ep.kv_fp32 = e->kv_fp32;
+        ep.max_pages = e->max_pages_per_slot;
+        ep.page_size = KV_PAGE;
+        ep.d = m.d;
+        ep.H = m.H;
+        ep.hd = m.hd;
+        if (gemm(Ly.qkv, &e->tm_wact_d, m.d, ep)) return -1;
+        if (launch_attn(e, Ly, rows, W, max_ctx, st)) return -1;
+        GemmEpilogue er;
+        er.mode = EPI_RESID;
+        er.bias = Ly.b_out;
+        er.x = e->wx;
+        er.ld_out = m.d;
+        if (gemm(Ly.out, &e->tm_wact_d, m.d, er)) return -1;
+        if (launch_ln(e, e->wx, nullptr, W, Ly.ln2_g, Ly.ln2_b, rows, st)) return -1;
+        GemmEpilogue ea;
+        ea.mode = EPI_ACT;
+        ea.bias = Ly.b_ff1;
+        ea.act = e->wact_f;
+        ea.ld_out = m.F;
+        ea.act_kind = 1;
+        ea.bpad_out = W;
+        if (gemm(Ly.ff1, &e->tm_wact_d, m.d, ea)) return -1;
+        GemmEpilogue e2;
+        e2.mode = EPI_RESID;
+        e2.bias = Ly.b_ff2;
+        e2.x = e->wx;
+        e2.ld_out = m.d;
+        if (gemm(Ly.ff2, &e->tm_wact_f, m.F, e2)) return -1;
     }
     return 0;
 }
@@ -703,6 +810,7 @@ int vcb_create(const vcb_config* cfg, vcb_engine** out) {
     if (getenv("VCB_GEMM_STAGES")) e->opt_gemm_stages = atoi(getenv("VCB_GEMM_STAGES"));
     if (getenv("VCB_PREFETCH")) e->opt_prefetch = atoi(getenv("VCB_PREFETCH"));
     if (getenv("VCB_ATT_BALANCE")) e->opt_att_balance = atoi(getenv("VCB_ATT_BALANCE"));
+    if (getenv("VCB_PREFILL_WIDE")) e->opt_prefill_wide = atoi(getenv("VCB_PREFILL_WIDE"));
     if (const char* sp = getenv("VCB_SPLITS")) {
         int n = 0, k = 0, sv = 0, used = 0;
         while (sscanf(sp, "%dx%d:%d%n", &n, &k, &sv, &used) == 3) {
@@ -730,7 +838,7 @@ int vcb_destroy(vcb_engine* e) {
     cudaFree(e->h1.w);
     for (auto& M : e->h2) cudaFree(M.w);
     void* ptrs[] = {e->b_h1, e->d_h2_maps, e->d_bias2, e->d_E_audio, e->pe, e->x_rows, e->qbuf, e->logits, e->att_ws, e->att_cnt, e->ln_stats, e->chain_ctr, e->x_slot, e->h_slot,
-                    e->act_d, e->act_d2, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->row_page, e->row_pages, e->all_rows, e->page_table,
+                    e->act_d, e->act_d2, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->row_page, e->row_pages, e->all_rows, e->page_table, e->wx, e->wq, e->w_att_ws, e->w_att_cnt, e->wact_d, e->wact_f,
                     e->d_slots, e->tok_log, e->dbg_logits, e->st, e->gr, e->d_seqs};
     for (void* p : ptrs) cudaFree(p);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1033,6 +1141,43 @@ int vcb_prefill(vcb_engine* e, const vcb_prompt* prompts, int32_t n, void* strea
     VCB_CUDA_OK(cudaMemcpy(t_slot, r_slot.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
     VCB_CUDA_OK(cudaMemcpy(t_last, r_last.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
     VCB_CUDA_OK(cudaMemcpy(t_page, r_page.data(), total_rows * sizeof(int), cudaMemcpyHostToDevice));
+    // ---- wide prefill: thousands of rows per pass through the rows-as-M GEMM ------------------------------
+    if (wide_usable(e) && total_rows >= static_cast<size_t>(e->opt_prefill_wide)) {
+        if (!e->wide_rows) e->wide_rows = static_cast<int>(std::min<size_t>(4096, (e->all_rows_cap + 127) / 128 * 128));
+        if (wide_alloc(e)) return -1;
+        const size_t W = static_cast<size_t>(e->wide_rows);
+        e->cur_q = e->wq;
+        e->cur_act_d = e->wact_d;
+        e->cur_att_ws = e->w_att_ws;
+        e->cur_att_cnt = e->w_att_cnt;
+        int rc = 0;
+        for (size_t off = 0; off < total_rows && !rc; off += W) {
+            const int rows = static_cast<int>(std::min<size_t>(W, total_rows - off));
+            e->cur_slot = t_slot + off;
+            e->cur_pos = t_pos + off;
+            e->cur_last = t_last + off;
+            e->cur_page = t_page + off;
+            e->cur_pages = nullptr;
+            embed_rows_kernel<<<rows, 256, 0, st>>>(e->d_seqs, t_seq + off, t_pos + off, e->wx, m.d, m.K, e->E_text,
+                                                    e->d_E_audio, e->mask_emb, e->pe, e->alpha_t, e->alpha_a);
+            LAUNCH_COUNT(e);
+            int max_ctx = 1;
+            for (int r = 0; r < rows; ++r) max_ctx = std::max(max_ctx, r_pos[off + r] + 1);
+            rc = forward_rows_wide(e, rows, max_ctx, st);
+            if (!rc) {
+                ProfScope ps(e, PC_LN, st);
+                gather_rows_kernel<<<rows, 256, 0, st>>>(e->wx, e->h_slot, e->cur_last, m.d);
+                LAUNCH_COUNT(e);
+            }
+        }
+        e->cur_q = nullptr;
+        e->cur_act_d = nullptr;
+        e->cur_att_ws = nullptr;
+        e->cur_att_cnt = nullptr;
+        if (rc) return -1;
+        VCB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     for (size_t off = 0; off < total_rows; off += vcb_engine::MAX_ROWS) {
         const int rows = static_cast<int>(std::min<size_t>(vcb_engine::MAX_ROWS, total_rows - off));
         e->cur_slot = t_slot + off;
@@ -1201,6 +1346,35 @@ int vcb_debug_gemm(const float* W_dev, const float* X_dev, float* out_dev, int32
     g.ep.mode = EPI_LOGITS; g.ep.bias = zb; g.ep.out = out_dev; g.ep.ld_out = N; g.ep.col_off = 0;
     g.Nout = N; g.Kdim = Kd; g.ldx = Kd; g.bpad = bpad; g.splits = splits; g.nvalid = B; g.simt = simt;
     if (gemm_launch(g, 0)) return -1;
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(w); cudaFree(x); cudaFree(zb);
+    return 0;
+}
+
+// Bring-up hook for the rows-as-M GEMM (gemm_rows.cu): out[r][n] = sum_k W[n][k] * X[r][k] for `rows` rows.
+int vcb_debug_gemm_rows(const float* W_dev, const float* X_dev, float* out_dev, int32_t N, int32_t Kd, int32_t rows) {
+    if (rows < 1 || !gemm_rows_supported(N, Kd, 0)) {
+        set_error("vcb_debug_gemm_rows: N %% 128 == 0, K %% 64 == 0, rows >= 1 required");
+        return -1;
+    }
+    const int rcap = (rows + 127) / 128 * 128;
+    __nv_bfloat16 *w = nullptr, *x = nullptr;
+    float* zb = nullptr;
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&w), packed_weight_elems(N, Kd) * 2));
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&x), static_cast<size_t>(2 * rcap) * Kd * 2));
+    VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&zb), static_cast<size_t>(N) * 4));
+    VCB_CUDA_OK(cudaMemset(x, 0, static_cast<size_t>(2 * rcap) * Kd * 2));
+    VCB_CUDA_OK(cudaMemset(zb, 0, static_cast<size_t>(N) * 4));
+    CUtensorMap tmW, tmX;
+    if (pack_weight(W_dev, w, N, Kd, &tmW)) return -1;
+    split_rows_kernel<<<dim3((Kd + 255) / 256, rows), 256>>>(X_dev, Kd, x, Kd, rcap);
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    if (make_tmap_bf16_2d(&tmX, x, 2 * rcap, Kd, Kd, 128)) return -1;
+    RowsGemmCall g;
+    g.tmX = &tmX; g.tmW = &tmW;
+    g.ep.mode = EPI_LOGITS; g.ep.bias = zb; g.ep.out = out_dev; g.ep.ld_out = N; g.ep.col_off = 0;
+    g.rows = rows; g.rcap = rcap; g.Nout = N; g.Kdim = Kd;
+    if (gemm_rows_launch(g, 0)) return -1;
     VCB_CUDA_OK(cudaDeviceSynchronize());
     cudaFree(w); cudaFree(x); cudaFree(zb);
     return 0;

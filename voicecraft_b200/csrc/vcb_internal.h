@@ -83,6 +83,16 @@ struct GemmCall {
     size_t pf_bytes = 0;
 };
 int gemm_launch(const GemmCall& g, cudaStream_t st);
+
+// Rows-as-M GEMM for prefill (gemm_rows.cu): activations [2][rcap][Kdim] (hi plane, lo plane), packed weights as above.
+struct RowsGemmCall {
+    const CUtensorMap* tmX = nullptr;   // activations: 2D [2*rcap rows][Kdim], box 128 rows x 64 cols
+    const CUtensorMap* tmW = nullptr;   // packed weights (pack_weight)
+    GemmEpilogue ep;                    // modes QKV / RESID / ACT / LOGITS; bpad_out = rows per plane of the ACT output
+    int rows = 0, rcap = 0, Nout = 0, Kdim = 0, pdl = 0;
+};
+bool gemm_rows_supported(int Nout, int Kdim, int hd);
+int gemm_rows_launch(const RowsGemmCall& g, cudaStream_t st);
 int gemm_pick_splits(int Nout, int Kdim, int num_sms);
 size_t packed_weight_elems(int N, int Kdim);
 int pack_weight(const float* w_f32_dev, __nv_bfloat16* out, int N, int Kdim, CUtensorMap* tm);
