@@ -168,13 +168,15 @@ def test_capacity_exhaustion_is_reported():
         m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), top_k=10)
 
 
-def test_full_size_830M_first_steps_match_oracle():
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_full_size_830M_first_steps_match_oracle(wide, monkeypatch):
     """BASELINE.json configs[1] at full size (giga830M: d=2048, 16 layers, 16 heads, K=4): prefill + the first sampling
     steps of one utterance, CUDA path (fp32 KV) vs the CPU oracle on the same synthetic checkpoint and the same Exp(1)
     noise.  Token ids identical, raw logits within LOGIT_TOL.  (Long generations at this size are covered by the
     size-independent checks: batched == single, generator stream, and scripts/parity_rate.py.)"""
     from oracle import lm_oracle
     from voicecraft_b200 import synthetic
+    monkeypatch.setenv("VCB_PREFILL_WIDE", wide)       # prompt through the narrow (0) / rows-as-M (1) prefill GEMM
     n_steps = 24
     cfg = synthetic.make_config("830M")
     sd = synthetic.make_state_dict(cfg, seed=3)

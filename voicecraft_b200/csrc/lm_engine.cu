@@ -111,7 +111,7 @@ struct vcb_engine {
     int opt_simt = 0, opt_pdl = 0, opt_profile = 0, opt_gemm_maxctas = 0, opt_gemm_stages = 0, opt_prefetch = 0, opt_att_balance = 1;
     // wide prefill (gemm_rows.cu): up to wide_rows prompt rows per pass through the layers, own activation planes;
     // opt_prefill_wide = minimum number of prompt rows that takes this path (0: never; VCB_PREFILL_WIDE)
-    int opt_prefill_wide = 0, wide_rows = 0;
+    int opt_prefill_wide = 256, wide_rows = 0;
     float *wx = nullptr, *wq = nullptr, *w_att_ws = nullptr;
     int* w_att_cnt = nullptr;
     __nv_bfloat16 *wact_d = nullptr, *wact_f = nullptr;
