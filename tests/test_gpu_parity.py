@@ -245,3 +245,18 @@ def test_wide_prefill_matches_reference_fixture(name, monkeypatch):
         diff = np.abs(got - ref)[live]
         assert int((diff > LOGIT_TOL).sum()) <= 1, f"step {step}: max {diff.max()}"
     assert np.array_equal(res.cpu().numpy(), g["res"]), "token ids differ from the reference fixture"
+
+
+def test_wide_prefill_bf16_kv_matches_oracle(monkeypatch):
+    """Default KV policy (bf16 pages) with the prompt going through the rows-as-M GEMM: its vectorised bf16 KV append must
+    round exactly like the oracle's kv_round_bf16 policy."""
+    from oracle import lm_oracle
+    monkeypatch.setenv("VCB_PREFILL_WIDE", "1")
+    name = "tts_topk40"
+    case = CASES[name]
+    cfg, sd, x, x_lens, y, g = gu.build_case(name, case)
+    oracle = lm_oracle.OracleLM(cfg, sd, kv_round_bf16=True)
+    kw = dict(case["kw"], silence_tokens=gu.SILENCE, kvcache=1, noise_fn=gu.cpu_noise_fn(case["seed"]))
+    ores = oracle.inference_tts(x, x_lens, y, **kw)[0]
+    res, _, _ = _run_case(name, case, "bf16")
+    assert np.array_equal(res.cpu().numpy(), ores.numpy())
