@@ -14,13 +14,15 @@
 // Split-K without a workspace: the S CTAs of a thread-block cluster each stream one K slice of the same 128-feature
 // weight tile (so >=128 CTAs pull HBM even for a 2048 x 2048 matrix), then reduce-scatter their accumulators
 // through distributed shared memory: CTA z owns token rows [z*R, (z+1)*R), every CTA writes its partial of those
-// rows into the owner's smem (st.shared::cluster), one cluster barrier, the owner sums the S partials in fixed
-// order (deterministic) and applies the fused epilogue:
+// rows into the owner's smem with asynchronous stores that count their bytes on the owner's mbarrier (st.async ...
+// mbarrier::complete_tx): the owner waits on its own barrier -- no cluster barrier after the start-up one -- then sums
+// the S partials in fixed order (deterministic) and applies the fused epilogue:
 //     EPI_QKV    q -> fp32 buffer, k/v -> appended to the paged KV cache    (activation.py:86-88, 626-631)
 //     EPI_RESID  x += y + bias                                            (transformer.py:321-329)
 //     EPI_ACT    ReLU / exact GELU -> bf16 hi/lo rows of the next GEMM      (transformer.py:387, voicecraft.py:183)
 //     EPI_LOGITS fp32 logits                                              (voicecraft.py:1085)
-// Warp roles: w0 TMA producer, w1 TMEM alloc + MMA issuer (one elected thread issues tcgen05.mma), w2..w5 epilogue.
+// Warp roles: w0 TMA producer, w1 TMEM alloc + MMA issuer (one elected thread issues tcgen05.mma), w2..w5 epilogue
+// (plus w6..w9 for tiles with >= 64 token rows).  Prompt batches use the rows-as-M kernel in gemm_rows.cu instead.
 #include "vcb_internal.h"
 
 #include <algorithm>
