@@ -72,6 +72,34 @@ def test_nondefault_delays_and_flatten():
         assert np.array_equal(v.numpy(), ov) and np.array_equal(i.numpy(), oi) and np.array_equal(m.numpy(), om), kw
 
 
+def test_random_shapes_package_equals_oracle_and_roundtrips():
+    """Property check over random (B, K, T) including the degenerate ones (T = 1, K = 1) and non-default options:
+    the package's vectorised index tables equal the oracle's step-by-step restatement, and revert(build(z)) == z."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 3), st.integers(1, 8), st.integers(1, 33), st.integers(0, 3), st.integers(0, 2), st.integers(0, 10 ** 6))
+    def check(B, K, T, flatten_first, empty_initial, seed):
+        rng = np.random.RandomState(seed)
+        z = rng.randint(0, 2048, size=(B, K, T)).astype(np.int64)
+        kw = dict(flatten_first=flatten_first, empty_initial=empty_initial)
+        pat = DelayedPatternProvider(K, **kw).get_pattern(T)
+        v, i, m = pat.build_pattern_sequence(torch.from_numpy(z), 2048)
+        ov, oi, om = patterns_oracle.build_pattern_sequence(z, 2048, **kw)
+        assert np.array_equal(v.numpy(), ov) and np.array_equal(i.numpy(), oi) and np.array_equal(m.numpy(), om)
+        rv, _, rm = pat.revert_pattern_sequence(v, 2048)
+        assert rv.shape == (B, K, T)
+        assert bool(rm.all()) and np.array_equal(rv.numpy(), z)
+
+    check()
+
+
+def test_empty_sequence_raises_like_the_reference():
+    """T = 0: the reference indexes an empty tensor and raises IndexError (codebooks_patterns.py:163-170); so does the package."""
+    z = torch.zeros(1, 4, 0, dtype=torch.int64)
+    with pytest.raises(IndexError):
+        DelayedPatternProvider(4).get_pattern(0).build_pattern_sequence(z, 2048)
+
 @pytest.mark.gpu
 def test_device_delay_kernel_matches_oracle():
     rng = np.random.RandomState(3)
