@@ -76,6 +76,24 @@ CASES = [
          kw=dict(top_k=20, top_p=1.0, temperature=1.0, stop_repetition=-1), eog_bias=3.0),
 ]
 
+# second batch (sampler corner cases, K = 8 in the batch / edit loops); generated with --only so the first batch's files
+# stay byte-identical
+CASES += [
+    dict(name="tts_topk_all", cfg="tiny", kind="tts", text_len=4, prompt=11, seed=31,
+         kw=dict(top_k=5000, top_p=1.0, temperature=1.0, stop_repetition=3)),          # top_k > vocabulary
+    dict(name="tts_temp03", cfg="tiny", kind="tts", text_len=5, prompt=13, seed=32,
+         kw=dict(top_k=0, top_p=1.0, temperature=0.3, stop_repetition=3)),             # temperature only
+    dict(name="tts_topp_tiny", cfg="tiny", kind="tts", text_len=4, prompt=10, seed=33,
+         kw=dict(top_k=0, top_p=0.05, temperature=1.0, stop_repetition=3)),            # keeps min_tokens_to_keep = 1
+    dict(name="tts_norep_sil", cfg="tiny", kind="tts", text_len=5, prompt=12, seed=34, silence_bias=True,
+         kw=dict(top_k=40, top_p=1.0, temperature=1.0, stop_repetition=-1)),           # penalty disabled, silence repeats
+    dict(name="batch2_k8", cfg="tiny", over=dict(n_codebooks=8, eos=-1, n_special=3, reduced_eog=0), kind="batch",
+         text_len=4, prompt=12, seed=35, batch_size=2, kw=dict(top_k=25, top_p=1.0, temperature=1.0, stop_repetition=3)),
+    dict(name="edit1_k8", cfg="tiny", over=dict(n_codebooks=8, eos=-1, n_special=3, reduced_eog=0), kind="edit",
+         text_len=7, prompt=36, seed=36, spans=[(6, 13)], eog_bias=3.0,
+         kw=dict(top_k=30, top_p=1.0, temperature=1.0, stop_repetition=-1)),
+]
+
 SILENCE = [1388, 1898, 131]
 
 
@@ -98,11 +116,14 @@ def main():
     torch.set_num_threads(8)
     voicecraft, cbp = import_reference()
     from oracle import lm_oracle, patterns_oracle
+    only = None
+    if "--only" in sys.argv:          # regenerate just these LM cases and merge them into lm_cases.json
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
 
     # ---- pattern goldens (codebooks_patterns.py docstring :307-316 plus random cases) -------------
     pat = {}
     rng = np.random.RandomState(0)
-    for i, (K, T) in enumerate([(3, 4), (4, 6), (4, 1), (8, 13), (4, 150), (1, 5)]):
+    for i, (K, T) in enumerate([] if only else [(3, 4), (4, 6), (4, 1), (8, 13), (4, 150), (1, 5)]):
         z = rng.randint(0, 2048, size=(2, K, T)).astype(np.int64)
         prov = cbp.DelayedPatternProvider(n_q=K)
         vals, idx, msk = prov.get_pattern(T).build_pattern_sequence(torch.from_numpy(z), 2048, False)
@@ -114,12 +135,18 @@ def main():
         assert np.array_equal(rv.numpy(), orv) and np.array_equal(ri.numpy(), ori) and np.array_equal(rm.numpy(), orm)
         pat[f"z{i}"], pat[f"values{i}"], pat[f"indexes{i}"], pat[f"mask{i}"] = z, ov, oi, om
         pat[f"rvalues{i}"], pat[f"rindexes{i}"], pat[f"rmask{i}"] = orv, ori, orm
-    np.savez_compressed(os.path.join(HERE, "patterns.npz"), **pat)
-    print("patterns ok")
+    if not only:
+        np.savez_compressed(os.path.join(HERE, "patterns.npz"), **pat)
+        print("patterns ok")
 
     # ---- LM goldens -----------------------------------------------------------------------------
     meta = {}
+    if only:
+        with open(os.path.join(HERE, "lm_cases.json")) as f:
+            meta = json.load(f)
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         cfg, sd, x, x_lens, y = build_case(case)
         model = ref_model(voicecraft, cfg, sd)
         oracle = lm_oracle.OracleLM(cfg, sd)

@@ -17,6 +17,15 @@ import golden_util as gu
 pytestmark = pytest.mark.gpu
 CASES = gu.load_cases()
 LOGIT_TOL = 2e-3
+# Reference fixtures generated after the last GPU session of round 1 (sampler corner cases, K = 8 batch / edit): the CPU
+# oracle is pinned to them (tests/test_oracle_golden.py); their first hardware run reports XPASS / xfail instead of
+# deciding the suite.  Drop the marker once they have been seen green on a B200.
+FIRST_RUN = {"tts_topk_all", "tts_temp03", "tts_topp_tiny", "tts_norep_sil", "batch2_k8", "edit1_k8"}
+
+
+def _case_params(names):
+    mark = pytest.mark.xfail(reason="fixture not yet run on hardware", strict=False)
+    return [pytest.param(n, marks=mark) if n in FIRST_RUN else n for n in names]
 
 
 def _model(cfg, sd, kv="fp32"):
@@ -61,7 +70,7 @@ def _run_case(name, case, kv):
     return res, m.trace_logits, g
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", _case_params(sorted(CASES)))
 def test_tokens_match_reference_fixture_kv_fp32(name):
     res, trace, g = _run_case(name, CASES[name], "fp32")
     # logits first: a numerical bug shows up here before it flips a token
