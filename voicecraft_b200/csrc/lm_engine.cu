@@ -425,13 +425,18 @@ int wide_alloc(vcb_engine* e) {
         }
         return cudaMemset(*p, 0, n * sizeof(**p)) != cudaSuccess ? 1 : 0;
     };
-    if (dalloc(&e->wx, W * m.d) || dalloc(&e->wq, W * m.d) || dalloc(&e->wact_d, 2 * W * m.d) ||
-        dalloc(&e->wact_f, 2 * W * m.F) || dalloc(&e->w_att_ws, W * m.H * e->att_maxch * (m.hd + 2)) ||
-        dalloc(&e->w_att_cnt, W * m.H))
+    const bool ok = !(dalloc(&e->wx, W * m.d) || dalloc(&e->wq, W * m.d) || dalloc(&e->wact_d, 2 * W * m.d) ||
+                      dalloc(&e->wact_f, 2 * W * m.F) || dalloc(&e->w_att_ws, W * m.H * e->att_maxch * (m.hd + 2)) ||
+                      dalloc(&e->w_att_cnt, W * m.H)) &&
+                    !(make_tmap_bf16_2d(&e->tm_wact_d, e->wact_d, 2 * W, m.d, m.d, 128) ||
+                      make_tmap_bf16_2d(&e->tm_wact_f, e->wact_f, 2 * W, m.F, m.F, 128));
+    if (!ok) {      // all or nothing: `wx` doubles as the "allocated" flag
+        cudaFree(e->wx); cudaFree(e->wq); cudaFree(e->wact_d); cudaFree(e->wact_f); cudaFree(e->w_att_ws); cudaFree(e->w_att_cnt);
+        e->wx = e->wq = e->w_att_ws = nullptr;
+        e->wact_d = e->wact_f = nullptr;
+        e->w_att_cnt = nullptr;
         return -1;
-    if (make_tmap_bf16_2d(&e->tm_wact_d, e->wact_d, 2 * W, m.d, m.d, 128) ||
-        make_tmap_bf16_2d(&e->tm_wact_f, e->wact_f, 2 * W, m.F, m.F, 128))
-        return -1;
+    }
     return 0;
 }
 
