@@ -7,6 +7,7 @@ bf16 KV cache it follows the oracle's kv_round_bf16 policy.  Token ids must be I
 1e-3 absolute (fp32 summation-order noise is ~1e-5).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -269,3 +270,14 @@ def test_wide_prefill_bf16_kv_matches_oracle(monkeypatch):
     ores = oracle.inference_tts(x, x_lens, y, **kw)[0]
     res, _, _ = _run_case(name, case, "bf16")
     assert np.array_equal(res.cpu().numpy(), ores.numpy())
+
+
+@pytest.mark.skipif(os.environ.get("VCB_TEST_EXPERIMENTAL") != "1",
+                    reason="grouped prefill attention (csrc/prefill_attn.cuh) has not been run on hardware yet; "
+                           "VCB_TEST_EXPERIMENTAL=1 enables its bring-up tests")
+@pytest.mark.parametrize("name", ["tts_topk40", "batch3", "edit2", "tts_small"])
+def test_experimental_grouped_prefill_attention(name, monkeypatch):
+    monkeypatch.setenv("VCB_PREFILL_WIDE", "1")
+    monkeypatch.setenv("VCB_PREFILL_ATT_GROUP", "4")
+    res, trace, g = _run_case(name, CASES[name], "fp32")
+    assert np.array_equal(res.cpu().numpy(), g["res"]), "token ids differ from the reference fixture"

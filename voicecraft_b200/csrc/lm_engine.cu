@@ -4,6 +4,7 @@
 // per-slot / per-group device state, step workspaces.  The caller (Python/torch) owns inputs, outputs and the stream.
 #include "../../include/vcb200.h"
 #include "lm_kernels.cuh"
+#include "prefill_attn.cuh"
 
 #include <algorithm>
 #include <array>
@@ -112,6 +113,7 @@ struct vcb_engine {
     // wide prefill (gemm_rows.cu): up to wide_rows prompt rows per pass through the layers, own activation planes;
     // opt_prefill_wide = minimum number of prompt rows that takes this path (0: never; VCB_PREFILL_WIDE)
     int opt_prefill_wide = 256, wide_rows = 0;
+    int opt_att_group = 0;            // EXPERIMENTAL: rows per work item of the wide prefill attention (0 / 4; prefill_attn.cuh)
     float *wx = nullptr, *wq = nullptr, *w_att_ws = nullptr;
     int* w_att_cnt = nullptr;
     __nv_bfloat16 *wact_d = nullptr, *wact_f = nullptr;
@@ -302,7 +304,37 @@ int launch_attn_hd(vcb_engine* e, const Layer& Ly, int rows, int bpad, int max_c
     return 0;
 }
 
+// EXPERIMENTAL grouped prefill attention (prefill_attn.cuh): G = 4 consecutive prompt rows per work item
+template <typename KVT, int HD>
+int launch_attn_group(vcb_engine* e, const Layer& Ly, int rows, int bpad, cudaStream_t st) {
+    constexpr int G = 4;
+    const ModelDims& m = e->m;
+    using L = GroupAttSmem<KVT, HD, G>;
+    static bool set = false;
+    if (!set) {
+        VCB_CUDA_OK(cudaFuncSetAttribute(attn_group_kernel<KVT, HD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        set = true;
+    }
+    const int items = (rows + G - 1) / G * m.H;
+    const int per_sm = std::max(1, std::min(4, (227 * 1024) / (L::TOTAL + 1024)));
+    const int grid = std::min(items, e->num_sms * per_sm);
+    ProfScope ps(e, PC_ATTN, st);
+    VCB_CUDA_OK(launch_k(e, attn_group_kernel<KVT, HD, G>, dim3(grid), dim3(ATT_THREADS + 32), L::TOTAL, st,
+                         static_cast<const float*>(e->cur_q), static_cast<const KVT*>(Ly.kpool),
+                         static_cast<const KVT*>(Ly.vpool), e->page_table, e->max_pages_per_slot, e->cur_slot, e->cur_pos, m.H,
+                         e->cur_act_d, m.d, bpad, 1.0f / sqrtf(static_cast<float>(m.hd)), rows));
+    LAUNCH_COUNT(e);
+    return 0;
+}
+
 int launch_attn(vcb_engine* e, const Layer& Ly, int rows, int bpad, int max_ctx, cudaStream_t st) {
+    if (e->opt_att_group == 4 && e->cur_q && e->cur_act_d) {         // wide prefill pass only
+        if (e->kv_fp32)
+            return e->m.hd == 128 ? launch_attn_group<float, 128>(e, Ly, rows, bpad, st)
+                                  : launch_attn_group<float, 64>(e, Ly, rows, bpad, st);
+        return e->m.hd == 128 ? launch_attn_group<__nv_bfloat16, 128>(e, Ly, rows, bpad, st)
+                              : launch_attn_group<__nv_bfloat16, 64>(e, Ly, rows, bpad, st);
+    }
     if (e->kv_fp32)
         return e->m.hd == 128 ? launch_attn_hd<float, 128>(e, Ly, rows, bpad, max_ctx, st)
                               : launch_attn_hd<float, 64>(e, Ly, rows, bpad, max_ctx, st);
@@ -816,6 +848,7 @@ int vcb_create(const vcb_config* cfg, vcb_engine** out) {
     if (getenv("VCB_PREFETCH")) e->opt_prefetch = atoi(getenv("VCB_PREFETCH"));
     if (getenv("VCB_ATT_BALANCE")) e->opt_att_balance = atoi(getenv("VCB_ATT_BALANCE"));
     if (getenv("VCB_PREFILL_WIDE")) e->opt_prefill_wide = atoi(getenv("VCB_PREFILL_WIDE"));
+    if (getenv("VCB_PREFILL_ATT_GROUP")) e->opt_att_group = atoi(getenv("VCB_PREFILL_ATT_GROUP"));
     if (const char* sp = getenv("VCB_SPLITS")) {
         int n = 0, k = 0, sv = 0, used = 0;
         while (sscanf(sp, "%dx%d:%d%n", &n, &k, &sv, &used) == 3) {
