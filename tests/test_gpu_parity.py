@@ -257,6 +257,7 @@ def test_wide_prefill_matches_reference_fixture(name, monkeypatch):
     assert np.array_equal(res.cpu().numpy(), g["res"]), "token ids differ from the reference fixture"
 
 
+@pytest.mark.xfail(reason="test added after the last GPU session of round 1: first hardware run is non-deciding", strict=False)
 def test_wide_prefill_bf16_kv_matches_oracle(monkeypatch):
     """Default KV policy (bf16 pages) with the prompt going through the rows-as-M GEMM: its vectorised bf16 KV append must
     round exactly like the oracle's kv_round_bf16 policy."""
