@@ -65,3 +65,65 @@ def test_undelay_matches_oracle(K, G, seed):
     finally:
         oracle.c.n_codebooks = saved
     assert got.shape == (K, G) and np.array_equal(got, ref)
+
+
+def test_weight_norm_folding_matches_torch():
+    """audiocraft checkpoints store weight-normalised convolutions as (weight_g, weight_v); the engine wants plain weights."""
+    from voicecraft_b200.tokenizer import fold_weight_norm
+    torch.manual_seed(0)
+    for mod in (torch.nn.Conv1d(6, 10, 3), torch.nn.ConvTranspose1d(6, 10, 4, stride=2)):
+        wn = torch.nn.utils.weight_norm(mod)              # old-style parametrisation: the checkpoint's key layout
+        with torch.no_grad():
+            wn.weight_g.mul_(torch.rand_like(wn.weight_g) + 0.5)
+        x = torch.randn(2, 6, 9)
+        ref = wn(x)
+        w = fold_weight_norm(wn.weight_g.detach(), wn.weight_v.detach())
+        plain = type(mod)(6, 10, mod.kernel_size[0], stride=mod.stride[0])
+        with torch.no_grad():
+            plain.weight.copy_(w)
+            plain.bias.copy_(wn.bias)
+        assert torch.allclose(plain(x), ref, atol=1e-6)
+
+
+def test_audiocraft_checkpoint_key_mapping_default_config():
+    """decoder.model.{i} indices of the SEANet decoder (conv 0, LSTM 1, per ratio [ELU, convtr, resblock], [ELU, conv]):
+    for the 4-ratio / 1-residual-layer config the transposed convs sit at 3, 6, 9, 12 and the output conv at 15, as in the
+    published EnCodec checkpoints.  Every checkpoint tensor must be consumed, every engine tensor produced."""
+    from oracle import encodec_oracle as eo
+    from voicecraft_b200.tokenizer import state_dict_from_audiocraft
+    cfg = eo.default_config()
+    shapes = eo.weight_shapes(cfg)
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+
+    def wn(prefix, shape):
+        sd[prefix + ".weight_g"] = torch.rand(shape[0], *([1] * (len(shape) - 1)), generator=g) + 0.5
+        sd[prefix + ".weight_v"] = torch.randn(*shape, generator=g)
+        sd[prefix + ".bias"] = torch.randn(shape[0] if "convtr" not in prefix else shape[1], generator=g)
+    for q in range(cfg.n_q):
+        sd[f"quantizer.vq.layers.{q}._codebook.embed"] = torch.randn(*shapes[f"vq.{q}.embed"], generator=g)
+    wn("decoder.model.0.conv.conv", shapes["dec.conv_in.weight"])
+    for l in range(cfg.lstm):
+        for part in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            sd[f"decoder.model.1.lstm.{part}_l{l}"] = torch.randn(*shapes[f"dec.lstm.{part}_l{l}"], generator=g)
+    for i, (ct, rb) in enumerate([(3, 4), (6, 7), (9, 10), (12, 13)]):
+        wn(f"decoder.model.{ct}.convtr.convtr", shapes[f"dec.up{i}.convtr.weight"])
+        wn(f"decoder.model.{rb}.block.1.conv.conv", shapes[f"dec.up{i}.res0.conv1.weight"])
+        wn(f"decoder.model.{rb}.block.3.conv.conv", shapes[f"dec.up{i}.res0.conv2.weight"])
+        wn(f"decoder.model.{rb}.shortcut.conv.conv", shapes[f"dec.up{i}.res0.shortcut.weight"])
+    wn("decoder.model.15.conv.conv", shapes["dec.conv_out.weight"])
+
+    class Recorder(dict):
+        def __init__(self, d):
+            super().__init__(d)
+            self.used = set()
+
+        def __getitem__(self, k):
+            self.used.add(k)
+            return super().__getitem__(k)
+    rec = Recorder(sd)
+    out = state_dict_from_audiocraft(rec, cfg)
+    assert set(out) == set(shapes)
+    for k, shp in shapes.items():
+        assert tuple(out[k].shape) == tuple(shp), k
+    assert rec.used == set(sd), sorted(set(sd) - rec.used)
