@@ -265,19 +265,21 @@ def main():
             lib.vcb_set_option(eng, b"profile", 1)
             for _ in range(nprof):
                 sess.step()
-            msb = (C.c_double * 6)()
-            cnt = (C.c_int64 * 6)()
-            lib.vcb_profile_read(eng, msb, cnt, 6)
+            msb = (C.c_double * 7)()
+            cnt = (C.c_int64 * 7)()
+            lib.vcb_profile_read(eng, msb, cnt, 7)
             lib.vcb_set_option(eng, b"profile", 0)
             names = ["gemm_w_xT_cluster(tcgen05, cluster split-K)", "attn_rows_kernel(paged KV, TMA bulk, split ctx)",
-                     "ln_rows_kernel", "(unused)", "sampler_kernel", "step_prep"]
+                     "ln_rows_kernel", "(unused)", "sampler_kernel", "step_prep", "mega_step_kernel(persistent decode step)"]
             total = sum(msb)
             shares = {names[i]: {"ms_per_step": msb[i] / nprof, "launches_per_step": cnt[i] / nprof, "share": msb[i] / total}
-                      for i in range(6)}
+                      for i in range(7)}
             S_prof = ctx1 + nprof / 2.0
             L = cfg.num_decoder_layers
-            dom = 1 if msb[1] >= msb[0] else 0
-            if dom == 1:
+            dom = max(range(7), key=lambda i: msb[i])
+            if dom == 6:
+                bytes_per_launch = sum(algorithmic_bytes(cfg, B, S_prof, kvb))     # the whole step is one launch
+            elif dom == 1:
                 bytes_per_launch = B * (S_prof + 1) * 2 * cfg.d_model * kvb      # K+V rows of every cached token, one layer
             else:
                 bytes_per_launch = Wb / (cnt[0] / nprof)                          # mean weight bytes per GEMM launch

@@ -45,3 +45,27 @@ def cpu_noise_fn(seed):
         q = torch.empty(shape, dtype=torch.float32).exponential_(1, generator=gen)
         return q if device is None else q.to(device)
     return fn
+
+
+# ---- headline shape (giga830M, 32 independent utterances): tests/golden/make_golden_830m.py ---------------------------
+def headline_fixture():
+    with open(os.path.join(GOLDEN, "lm_830m_b32.json")) as f:
+        meta = json.load(f)
+    return meta, np.load(os.path.join(GOLDEN, "lm_830m_b32.npz"))
+
+
+def suppress_end_tokens(cfg, sd):
+    """only the reference's length cap ends generation (bench.py does the same)"""
+    for k in range(cfg.n_codebooks):
+        sd[f"predict_layer.{k}.2.bias"][cfg.eos] = -1e4
+        sd[f"predict_layer.{k}.2.bias"][cfg.eog] = -1e4
+    return sd
+
+
+def headline_checkpoint(seed):
+    cfg = synthetic.make_config("830M")
+    return cfg, suppress_end_tokens(cfg, synthetic.make_state_dict(cfg, seed=seed))
+
+
+def headline_utterance(cfg, meta, i):
+    return synthetic.synthetic_utterance(cfg, 100 + i, meta["text_len"], meta["prompts"][i % len(meta["prompts"])])

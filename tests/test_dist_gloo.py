@@ -44,8 +44,11 @@ def test_partition_is_a_balanced_exact_cover():
         assert max(loads) <= sum(lengths) / world + max(lengths)
 
 
-def test_world2_gloo_gather():
-    lengths = [37, 5, 64, 12, 1, 29, 30]
+import pytest
+
+
+@pytest.mark.parametrize("lengths", [[37, 5, 64, 12, 1, 29, 30], [17]])       # [17]: one utterance, rank 1 holds nothing
+def test_world2_gloo_gather(lengths):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

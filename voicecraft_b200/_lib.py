@@ -30,12 +30,14 @@ class vcb_sampling(C.Structure):
 class vcb_prompt(C.Structure):
     _fields_ = [("slot", C.c_int32), ("n_copies", C.c_int32), ("mode", C.c_int32), ("x_len", C.c_int32),
                 ("text_ids_dev", C.c_void_p), ("y_len", C.c_int32), ("y_tokens_dev", C.c_void_p),
-                ("mask_rows_dev", C.c_void_p), ("n_more_spans", C.c_int32), ("more_mask_rows", C.c_int32 * 8)]
+                ("mask_rows_dev", C.c_void_p), ("n_more_spans", C.c_int32), ("more_mask_rows", C.c_int32 * 8),
+                ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64), ("rng_threads", C.c_int32), ("rng_reserved", C.c_int32)]
 
 
 class vcb_status(C.Structure):
     _fields_ = [("done", C.c_int32), ("forced", C.c_int32), ("n_steps", C.c_int32), ("keep", C.c_int32),
-                ("n_spans_done", C.c_int32), ("span_ends", C.c_int32 * 8)]
+                ("n_spans_done", C.c_int32), ("span_ends", C.c_int32 * 8), ("reserved", C.c_int32),
+                ("rng_offset", C.c_uint64)]
 
 
 # every symbol include/vcb200.h (and include/vcb200_codec.h) declares, with its prototype
@@ -54,6 +56,7 @@ PROTOTYPES = {
     "vcb_read_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p]),
     "vcb_release": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "vcb_debug_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "vcb_debug_exponential": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
     "vcb_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "vcb_debug_gemm_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "vcb_timeline": (C.c_int, [C.c_int32, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]),

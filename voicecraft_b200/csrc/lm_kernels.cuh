@@ -411,11 +411,14 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
                  const float* __restrict__ x_slot, float* __restrict__ x_rows, int d,
                  const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats,
                  const int* __restrict__ page_table, int max_pages, int* __restrict__ row_page,
-                 int* __restrict__ row_pages) {
+                 int* __restrict__ row_pages, int* __restrict__ row_forced, unsigned int* __restrict__ phase_flags,
+                 int n_phase_flags) {
     __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x;
+    if (r == 0)                                  // completion counters of the persistent step kernel (mega_step.cu)
+        for (int i = threadIdx.x; i < n_phase_flags; i += blockDim.x) phase_flags[i] = 0u;
     const int slot = slots[r];
     __shared__ int s_pos;
     if (threadIdx.x == 0) {
@@ -426,6 +429,7 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
         row_pos[r] = s_pos;
         row_last[r] = on ? slot : -1;
         row_page[r] = on ? page_table[slot * max_pages + s_pos / KV_PAGE] : 0;
+        row_forced[r] = S.forced;           // snapshot for the sampler's K CTAs of this slot (they are not ordered)
         if (on) {
             S.seq_len += 1;
             S.y_len += 1;
@@ -476,14 +480,63 @@ __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Exp(1) noise of `torch.multinomial` generated in place (voicecraft.py:85: multinomial(p, 1) == argmax(p / q),
+// q = empty_like(p).exponential_(1)).  Bit-identical to ATen's CUDA path for a draw of `numel` fp32 elements from a
+// Philox generator at (seed, offset): distribution_nullary_kernel launches T = 256 * grid threads, thread `idx` runs
+// curand_init(seed, idx, offset) and element li of loop iteration `it` takes component (li % 4T) / T of the it-th
+// curand_uniform4 of thread (li % T); exponential_ maps u -> -log(u) with the u ~ 1 guard of
+// ATen/core/TransformationHelper.h.  (offset is a multiple of 4 in torch: one 128-bit Philox counter per call.)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float torch_exponential_at(unsigned long long seed, unsigned long long offset,
+                                                      unsigned int threads, unsigned long long li) {
+    const unsigned long long per_iter = 4ull * threads;
+    const unsigned long long it = li / per_iter, rem = li - it * per_iter;
+    const unsigned int comp = static_cast<unsigned int>(rem / threads);
+    const unsigned long long idx = rem - static_cast<unsigned long long>(comp) * threads;
+    const unsigned long long ctr = offset / 4ull + it;          // curand_init skipahead(offset) + one counter per curand4
+    const uint4 o = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32),
+                                             static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32)),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const uint32_t x = comp == 0 ? o.x : comp == 1 ? o.y : comp == 2 ? o.z : o.w;
+    // curand_uniform: x * 2^-32 + 2^-33 (the product is exact, one rounding in the add), range (0, 1]
+    const float u = __fadd_rn(__fmul_rn(static_cast<float>(x), 2.3283064365386963e-10f), 1.16415321826934814453e-10f);
+    const float lg = (u >= 1.0f - 1.1920928955078125e-07f / 2) ? -1.1920928955078125e-07f / 2 : logf(u);
+    return -lg;                                                 // (-1 / lambda) * log with lambda = 1
+}
+// philox offset consumed by one draw of numel elements (ATen calc_execution_policy: counter_offset)
+__host__ __device__ inline unsigned long long torch_draw_offset(unsigned long long numel, unsigned int threads) {
+    return ((numel - 1) / (4ull * threads) + 1) * 4ull;
+}
+
+__global__ void debug_exponential_kernel(float* out, unsigned long long numel, unsigned long long seed,
+                                         unsigned long long offset, unsigned int threads) {
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < numel;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+        out[i] = torch_exponential_at(seed, offset, threads, i);
+}
+
 struct SamplerArgs {
     const int* slots;
+    const int* row_forced;    // per listed slot: SlotState::forced as of the step prologue (null: read the slot)
     int n;
     SlotState* st;
     GroupState* gr;
     const float* logits;      // [n][ldl] fp32 (bias included), column = k*Vpad + v
     int ldl;
-    const float* noise;       // [n*K][V]
+    const float* noise;       // [n*K][V], or null: generated from the group's Philox stream (GroupState::rng_*)
     float* dbg_logits;        // [n*K][V] or null
     int* tok_log;             // [max_slots][max_steps][K]
     int max_steps, max_seq;
@@ -525,11 +578,14 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = a.K, V = a.V;
 
-    if (S.forced > 0) {
+    // `forced` as of the start of this step: the k == 0 CTA decrements S.forced below, and the K CTAs of a slot are not
+    // ordered against each other (they need not even be co-resident), so the decision is taken on a snapshot
+    const int forced_now = a.row_forced ? a.row_forced[i] : S.forced;
+    if (forced_now > 0) {
         // edit-mode hand-over to the next span (voicecraft.py:838-858): this forward fed a forced embedding,
         // nothing is sampled; prepare the next forced input.
         if (k != 0) return;
-        const int f = S.forced;                 // 2: next input = mask embedding, 1: next input = empty-token embedding
+        const int f = forced_now;               // 2: next input = mask embedding, 1: next input = empty-token embedding
         const float* pe = a.pe + static_cast<size_t>(S.y_len) * a.d;
         for (int c = tid; c < a.d; c += SAMP_THREADS) {
             float acc;
@@ -589,10 +645,22 @@ __global__ void __launch_bounds__(SAMP_THREADS) sampler_kernel(const SamplerArgs
 
     // the Exp(1) draws are independent of everything below: fetch them now, not after the softmax
     float nz[SAMP_MAXV];
+    if (a.noise) {
 #pragma unroll
-    for (int j = 0; j < SAMP_MAXV; ++j) {
-        const int v = tid + j * SAMP_THREADS;
-        nz[j] = (v < V) ? a.noise[static_cast<size_t>(row) * V + v] : 1.f;
+        for (int j = 0; j < SAMP_MAXV; ++j) {
+            const int v = tid + j * SAMP_THREADS;
+            nz[j] = (v < V) ? a.noise[static_cast<size_t>(row) * V + v] : 1.f;
+        }
+    } else {
+        // this group's own generator: the draw has the reference's shape [size*K, V], row = member*K + k
+        const unsigned long long seed = (static_cast<unsigned long long>(G.seed_hi) << 32) | G.seed_lo;
+        const unsigned long long off = (static_cast<unsigned long long>(G.off_hi) << 32) | G.off_lo;
+        const unsigned long long base = (static_cast<unsigned long long>(S.member) * K + k) * V;
+#pragma unroll
+        for (int j = 0; j < SAMP_MAXV; ++j) {
+            const int v = tid + j * SAMP_THREADS;
+            nz[j] = (v < V) ? torch_exponential_at(seed, off, G.rng_threads, base + v) : 1.f;
+        }
     }
 
     // ---- argmax of the edited logits (first index wins), needed for the end-token trigger ----------
@@ -858,6 +926,12 @@ __device__ void sampler_finish_slot(const SamplerArgs& a, int slot, float* sred)
     __threadfence();
     // ---- group finalize
     G.arrive = 0;
+    if (G.rng_threads) {                    // one draw of [size*K, V] consumed, whether or not the caller supplied noise
+        unsigned long long off = (static_cast<unsigned long long>(G.off_hi) << 32) | G.off_lo;
+        off += torch_draw_offset(static_cast<unsigned long long>(G.size) * K * a.V, G.rng_threads);
+        G.off_lo = static_cast<unsigned int>(off);
+        G.off_hi = static_cast<unsigned int>(off >> 32);
+    }
     if (G.n_eog == 0) {
         if (G.trig_keep > 0) {
             G.n_eog = 1;

@@ -1,0 +1,848 @@
+// Persistent decode-step kernel: every transformer layer of one decode step (QKV -> attention -> out-proj -> FFN1 -> FFN2,
+// x L, then the logit heads) in ONE launch on a grid of one CTA per SM.  (transformer.py:321-329, 473-488; activation.py:536-638;
+// voicecraft.py:181-185, 1085-1087.)
+//
+// Why (profiles/r01_timeline_all_v4.txt): as 84 separate kernels the step is latency-chain bound -- every
+// GEMM stops the HBM stream for a launch boundary, a pipeline ramp and an epilogue tail; 66 GEMM launches ran at 0.33 of the
+// HBM roofline.  Neither the weights nor the cached K/V pages depend on the activations of the step, so here ONE producer
+// thread per SM streams them, in schedule order, through a single ring of 16 KB shared-memory slots and never waits for
+// anything but a free slot: while a phase's dependency chain (flag -> activation tiles -> MMA -> split-K reduce -> epilogue
+// -> flag) resolves, the ring already fills with the next phases' weight blocks / KV slabs.
+//
+//   * work split ("stream-K"): a GEMM phase is the list of its 16 KB weight blocks (tile-major, k-minor); an attention
+//     phase is the list of (row, head, page) units.  CTA c takes the contiguous range [c*T/G, (c+1)*T/G) of either list:
+//     every SM streams the same number of bytes (+-1 block) per phase, whatever the matrix shape or the context lengths.
+//   * roles: warp 0 ring producer (weights + K/V, TMA), warp 1 MMA issuer (tcgen05, fp32 accumulators in TMEM, 4 stages),
+//     warp 2 activation (B operand) producer -- the only one that waits for the previous phase --, warps 4..11 workers
+//     (GEMM epilogues / attention math).
+//   * split-K without clusters: a CTA's partial of a tile goes to an L2-resident workspace; the last CTA to arrive
+//     (atomic counter) sums all partials in contributor order (deterministic) and runs the fused epilogue of
+//     gemm_tcgen05.cu (QKV append, residual + next LayerNorm operand and statistics, ReLU/GELU, logits).
+//   * phase hand-over: one completion counter per phase (tiles done / CTAs done), release/acquire at GPU scope; data that
+//     crossed CTAs is read with ld.global.cg (L1 is not coherent inside one kernel) or by TMA after fence.proxy.async.
+//   * attention: same math as attn_rows_kernel (lm_kernels.cuh), but the current token's k/v come from the QKV epilogue's
+//     fp32 side buffer (rounded like the cache), so the page stream has no dependency on this step at all; items split
+//     between CTAs are merged flash-decoding style by the last arriver, in CTA order.
+// All waits are bounded: a stuck wait records (role, phase, cta) in MegaArgs::dbg and traps instead of hanging the GPU.
+#include "vcb_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace vcb {
+
+static constexpr int MG_THREADS = 384;
+static constexpr int MG_WORKERS = 256;
+static constexpr int MG_SLOT = 16384;          // ring slot = one 128 x 64 bf16 weight block = one bf16 K (or V) slab
+static constexpr int MG_NS = 11;               // ring slots
+static constexpr int MG_NB = 6;                // activation (B operand) ring slots
+static constexpr int MG_BSLOT = 8192;          // 64 rows (32 hi + 32 lo) x 64 k, bf16
+static constexpr int MG_NACC = 4;              // TMEM accumulator stages
+static constexpr int MG_HD = 128;
+static constexpr int MG_PAGE = 64;
+
+struct MegaSmem {
+    static constexpr int RING = 0;
+    static constexpr int BRING = MG_NS * MG_SLOT;                  // attention scratch aliases this region
+    static constexpr int BAR = BRING + MG_NB * MG_BSLOT;
+    static constexpr int NBAR = 2 * MG_NS + 2 * MG_NB + 2 * MG_NACC;
+    static constexpr int MISC = BAR + NBAR * 8;                    // tmem slot, flags, page-count table
+    static constexpr int TOTAL = MISC + 16 + 34 * 4 + 64;
+    // attention scratch inside BRING
+    static constexpr int A_SC = 0;                                  // scores, double buffered: 2 x 64 floats
+    static constexpr int A_PW = 512;                                // per-warp probabilities: 8 x 64 floats
+    static constexpr int A_RED = A_PW + 8 * MG_PAGE * 4;            // per-warp partial outputs: 8 x 128 floats
+};
+static_assert(MegaSmem::A_RED + 8 * MG_HD * 4 <= MG_NB * MG_BSLOT, "attention scratch must fit the B ring");
+
+__device__ __forceinline__ unsigned int mg_ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mg_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long mg_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void mg_die(unsigned int* dbg, unsigned int role, unsigned int phase, unsigned int extra) {
+    if (dbg) {
+        if (atomicCAS(dbg, 0u, 1u) == 0u) {
+            dbg[1] = role;
+            dbg[2] = phase;
+            dbg[3] = blockIdx.x;
+            dbg[4] = extra;
+        }
+        __threadfence_system();
+    }
+    __trap();
+}
+// bounded mbarrier wait (2 s): a protocol bug surfaces as a CUDA error, not as a hung box
+__device__ __forceinline__ void mg_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, unsigned int role, unsigned int phase) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 1;; ++spins) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spins & 0xfffu) == 0) {
+            const unsigned long long t = mg_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) mg_die(dbg, role, phase, 0x100u | parity);
+        }
+    }
+}
+// bounded wait for a phase completion counter
+__device__ __forceinline__ void mg_wait_flag(const unsigned int* flag, unsigned int target, unsigned int* dbg, unsigned int role,
+                                             unsigned int phase) {
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0; mg_ld_acquire(flag) < target; ++spins) {
+        if ((spins & 0x3ffu) == 0x3ffu) {
+            const unsigned long long t = mg_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) mg_die(dbg, role, phase, 0x200u);
+        }
+    }
+}
+__device__ __forceinline__ void mg_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// range of CTA c over T work units, and the CTA that owns unit u
+__device__ __forceinline__ void mg_range(long long T, int c, int G, int& b0, int& b1) {
+    b0 = static_cast<int>(T * c / G);
+    b1 = static_cast<int>(T * (c + 1) / G);
+}
+__device__ __forceinline__ int mg_owner(long long u, long long T, int G) { return static_cast<int>(((u + 1) * G - 1) / T); }
+
+__device__ __forceinline__ uint2 mg_pack_bf16x4(float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&lo);
+    r.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return r;
+}
+__device__ __forceinline__ float mg_bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused epilogue of one output tile, run by the 256 worker threads of the CTA that arrived last.
+// Thread mapping: lane -> features 4*lane .. 4*lane+3 of the tile, warp wq -> rows wq*RPW .. wq*RPW+RPW-1.
+// ------------------------------------------------------------------------------------------------------------------------
+template <int BPAD>
+__device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPhase& P, int p, int tile, int c_first, int ncontrib,
+                                                 long long T, int G, int wq, int lane) {
+    constexpr int RPW = BPAD / 8;
+    const GemmEpilogue& ep = P.ep;
+    const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
+    const int m0 = tl * 128 + 4 * lane;                       // first of my 4 features (group-local)
+    const int Nout = P.Nout;
+    const int row_base = wq * RPW;
+    // ---- operands that do not depend on the reduction ------------------------------------------------------------------
+    const float* bias_ptr = P.grp_bias ? P.grp_bias[g] : ep.bias;
+    float bias[4], cv[4], gn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool ok = m0 + i < Nout;
+        bias[i] = ok ? bias_ptr[m0 + i] : 0.f;
+        cv[i] = (ok && ep.ln_fold) ? ep.cvec[m0 + i] : 0.f;
+        gn[i] = (ok && ep.emit) ? ep.next_gamma[m0 + i] : 0.f;
+    }
+    float mean[RPW], rstd[RPW];
+    float4 xold[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int row = row_base + rr;
+        mean[rr] = 0.f;
+        rstd[rr] = 0.f;
+        xold[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.ln_fold) {
+            float s1 = 0.f, s2 = 0.f;
+            if (row < A.nvalid)
+                for (int t = lane; t < ep.stats_tiles; t += 32) {
+                    const float2 v = __ldcg(reinterpret_cast<const float2*>(ep.stats + (static_cast<size_t>(t) * STATS_ROWS + row) * 2));
+                    s1 += v.x;
+                    s2 += v.y;
+                }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            mean[rr] = s1 * ep.inv_d;
+            rstd[rr] = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - mean[rr] * mean[rr], 0.f) + ep.ln_eps);
+        }
+        if (ep.mode == EPI_RESID && row < A.nvalid)
+            xold[rr] = __ldcg(reinterpret_cast<const float4*>(ep.x + static_cast<size_t>(row) * ep.ld_out + m0));
+    }
+    // ---- fixed-order sum of the partials (contributor = CTA order = ascending k) -------------------------------------------
+    float4 acc[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) acc[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int kb = P.kb;
+    for (int s0 = 0; s0 < ncontrib; s0 += 4) {
+        float4 v[4][RPW];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int s = s0 + j;
+            if (s < ncontrib) {
+                const int c = c_first + s;
+                const int cb0 = static_cast<int>(T * c / G);
+                const int seg = tile - cb0 / kb;
+                const float* src = A.part + (static_cast<size_t>(c) * MEGA_MAXSEG + seg) * BPAD * 128 + 4 * lane;
+#pragma unroll
+                for (int rr = 0; rr < RPW; ++rr) v[j][rr] = __ldcg(reinterpret_cast<const float4*>(src + (row_base + rr) * 128));
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < RPW; ++rr) v[j][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                acc[rr].x += v[j][rr].x;
+                acc[rr].y += v[j][rr].y;
+                acc[rr].z += v[j][rr].z;
+                acc[rr].w += v[j][rr].w;
+            }
+    }
+    // ---- epilogue ---------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int row = row_base + rr;
+        const bool row_ok = row < A.nvalid;                   // warp-uniform
+        float a[4] = {acc[rr].x, acc[rr].y, acc[rr].z, acc[rr].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (ep.ln_fold) a[i] = rstd[rr] * (a[i] - mean[rr] * cv[i]);
+            a[i] += bias[i];
+        }
+        float xn[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_ok) {
+            switch (ep.mode) {
+                case EPI_QKV: {
+                    const int pos = ep.row_pos[row];
+                    if (pos < 0 || m0 >= Nout) break;
+                    const int part = m0 / ep.d, cc = m0 - part * ep.d;
+                    if (part == 0) {
+                        __stcg(reinterpret_cast<float4*>(ep.qbuf + static_cast<size_t>(row) * ep.d + cc), make_float4(a[0], a[1], a[2], a[3]));
+                        break;
+                    }
+                    const int page = ep.row_page[row];
+                    const int h = cc / ep.hd, e = cc - h * ep.hd;
+                    const size_t off = ((static_cast<size_t>(page) * ep.H + h) * ep.page_size + pos % ep.page_size) * ep.hd + e;
+                    void* pool = (part == 1) ? ep.kpool : ep.vpool;
+                    float* side = (part == 1) ? ep.knew : ep.vnew;
+                    if (ep.kv_fp32) {
+                        __stcg(reinterpret_cast<float4*>(static_cast<float*>(pool) + off), make_float4(a[0], a[1], a[2], a[3]));
+                    } else {
+                        __stcg(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(pool) + off), mg_pack_bf16x4(a[0], a[1], a[2], a[3]));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a[i] = mg_bf16_round(a[i]);
+                    }
+                    __stcg(reinterpret_cast<float4*>(side + static_cast<size_t>(row) * ep.d + cc), make_float4(a[0], a[1], a[2], a[3]));
+                    break;
+                }
+                case EPI_RESID: {
+                    xn[0] = xold[rr].x + a[0];
+                    xn[1] = xold[rr].y + a[1];
+                    xn[2] = xold[rr].z + a[2];
+                    xn[3] = xold[rr].w + a[3];
+                    if (m0 < Nout)
+                        __stcg(reinterpret_cast<float4*>(ep.x + static_cast<size_t>(row) * ep.ld_out + m0), make_float4(xn[0], xn[1], xn[2], xn[3]));
+                    break;
+                }
+                case EPI_ACT: {
+                    if (m0 >= Nout) break;
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v = a[i];
+                        if (ep.act_kind == 1) v = fmaxf(v, 0.f);
+                        else if (ep.act_kind == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+                        hi[i] = mg_bf16_round(v);
+                        lo[i] = v - hi[i];
+                    }
+                    __stcg(reinterpret_cast<uint2*>(ep.act + static_cast<size_t>(row) * ep.ld_out + m0), mg_pack_bf16x4(hi[0], hi[1], hi[2], hi[3]));
+                    __stcg(reinterpret_cast<uint2*>(ep.act + static_cast<size_t>(row + ep.bpad_out) * ep.ld_out + m0),
+                           mg_pack_bf16x4(lo[0], lo[1], lo[2], lo[3]));
+                    break;
+                }
+                default: {
+                    float* o = ep.out + static_cast<size_t>(row) * ep.ld_out + ep.col_off + g * P.col_grp_stride + m0;
+                    if (m0 + 3 < Nout) {
+                        __stcg(reinterpret_cast<float4*>(o), make_float4(a[0], a[1], a[2], a[3]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (m0 + i < Nout) __stcg(o + i, a[i]);
+                    }
+                }
+            }
+        }
+        if (ep.emit) {
+            // next GEMM's operand gamma_next * x_new (hi/lo) and this tile's (sum x, sum x^2) of the row: a warp holds
+            // exactly the 128 features of the tile for this row
+            float p1 = 0.f, p2 = 0.f;
+            if (row_ok && m0 < Nout) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = gn[i] * xn[i];
+                    hi[i] = mg_bf16_round(v);
+                    lo[i] = v - hi[i];
+                    p1 += xn[i];
+                    p2 += xn[i] * xn[i];
+                }
+                __stcg(reinterpret_cast<uint2*>(ep.next_act + static_cast<size_t>(row) * ep.next_ld + m0), mg_pack_bf16x4(hi[0], hi[1], hi[2], hi[3]));
+                __stcg(reinterpret_cast<uint2*>(ep.next_act + static_cast<size_t>(row + ep.next_bpad) * ep.next_ld + m0),
+                       mg_pack_bf16x4(lo[0], lo[1], lo[2], lo[3]));
+            }
+            p1 = warp_sum(p1);
+            p2 = warp_sum(p2);
+            if (lane == 0 && row_ok)
+                __stcg(reinterpret_cast<float2*>(ep.stats_out + (static_cast<size_t>(tl) * STATS_ROWS + row) * 2), make_float2(p1, p2));
+        }
+    }
+}
+
+// K / V element loads from a ring slot (same conversions as lm_kernels.cuh::load_kv_vec)
+template <typename KVT, int N>
+__device__ __forceinline__ void mg_load_kv(const KVT* p, float (&out)[N]) {
+    if constexpr (sizeof(KVT) == 2) {
+        if constexpr (N == 8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                out[2 * i] = __uint_as_float(w[i] << 16);
+                out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+        } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(p);
+            out[0] = __uint_as_float(u.x << 16);
+            out[1] = __uint_as_float(u.x & 0xffff0000u);
+            out[2] = __uint_as_float(u.y << 16);
+            out[3] = __uint_as_float(u.y & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(p + i);
+            out[i] = f.x;
+            out[i + 1] = f.y;
+            out[i + 2] = f.z;
+            out[i + 3] = f.w;
+        }
+    }
+}
+
+template <int BPAD, typename KVT>
+__global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_constant__ MegaArgs A) {
+    constexpr int BN = 2 * BPAD;                          // UMMA N: hi rows + lo rows
+    constexpr int HB = BPAD / 2;                          // rows per worker group in the TMEM read-out
+    constexpr int B_BYTES = BN * 64 * 2;
+    constexpr int TPS = MG_SLOT / (MG_HD * static_cast<int>(sizeof(KVT)));   // tokens per ring slot: 64 (bf16) / 32 (fp32)
+    constexpr int NSL = MG_PAGE / TPS;                    // ring slots per K (or V) slab
+    using L = MegaSmem;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* ring = smem + L::RING;
+    uint8_t* bring = smem + L::BRING;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR);
+    uint64_t* empty = full + MG_NS;
+    uint64_t* bfull = empty + MG_NS;
+    uint64_t* bempty = bfull + MG_NB;
+    uint64_t* accfull = bempty + MG_NB;
+    uint64_t* accempty = accfull + MG_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::MISC);
+    int* s_flag = reinterpret_cast<int*>(smem + L::MISC + 8);
+    int* s_cum = reinterpret_cast<int*>(smem + L::MISC + 16);           // [33] prefix sum of pages per row
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cta = blockIdx.x, G = gridDim.x;
+    const MegaPhase* __restrict__ ph = A.ph;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < MG_NS; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 8);          // weights: 7 lanes of the MMA warp + its commit; K/V slabs: the 8 worker warps
+        }
+        for (int i = 0; i < MG_NB; ++i) {
+            mbar_init(&bfull[i], 1);
+            mbar_init(&bempty[i], 1);
+        }
+        for (int i = 0; i < MG_NACC; ++i) {
+            mbar_init(&accfull[i], 1);
+            mbar_init(&accempty[i], 8);
+        }
+        mbar_fence_init();
+        int c = 0;
+        for (int r = 0; r < 32; ++r) {
+            s_cum[r] = c;
+            const int pos = r < A.nvalid ? A.row_pos[r] : -1;
+            c += pos >= 0 ? pos / MG_PAGE + 1 : 0;
+        }
+        s_cum[32] = c;
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const long long U = static_cast<long long>(A.H) * s_cum[32];     // attention units of this step
+    int u0, u1;
+    mg_range(U, cta, G, u0, u1);
+    const int att_items = (u1 - u0) * 2 * NSL;                        // ring items of one attention phase (this CTA)
+
+    if (warp == 0) {
+        // ===== ring producer: weight blocks and K/V slabs of every phase, in schedule order ==============================
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            uint32_t it = 0;
+            auto acquire = [&](int p) -> int {
+                const int s = it % MG_NS;
+                if (it >= MG_NS) mg_wait(&empty[s], ((it / MG_NS) - 1) & 1, A.dbg, 0, p);
+                ++it;
+                return s;
+            };
+            for (int p = 0; p < A.nph; ++p) {
+                const MegaPhase& P = ph[p];
+                if (P.type == MEGA_GEMM) {
+                    const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
+                    int b0, b1;
+                    mg_range(T, cta, G, b0, b1);
+                    for (int blk = b0; blk < b1; ++blk) {
+                        const int tile = blk / P.kb, kbi = blk - tile * P.kb;
+                        const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
+                        const int s = acquire(p);
+                        mbar_arrive_expect_tx(&full[s], MG_SLOT);
+                        tma_load_2d_hint(ring + s * MG_SLOT, P.tmA + g, &full[s], 0, (tl * P.kb + kbi) * 128, pol);
+                    }
+                } else {
+                    // units are ordered (row, head, page); walk my range
+                    int r = 0;
+                    while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u0) ++r;
+                    int npg = s_cum[r + 1] - s_cum[r];
+                    int rem = u0 - A.H * s_cum[r];
+                    int h = npg ? rem / npg : 0, pg = npg ? rem - h * npg : 0;
+                    const KVT* kpool = static_cast<const KVT*>(P.kpool);
+                    const KVT* vpool = static_cast<const KVT*>(P.vpool);
+                    for (int u = u0; u < u1; ++u) {
+                        const int page = A.row_pages[r * A.max_pages + pg];
+                        const size_t off = (static_cast<size_t>(page) * A.H + h) * MG_PAGE * MG_HD;
+#pragma unroll
+                        for (int kv = 0; kv < 2; ++kv) {
+                            const KVT* src = (kv == 0 ? kpool : vpool) + off;
+#pragma unroll
+                            for (int j = 0; j < NSL; ++j) {
+                                const int s = acquire(p);
+                                mbar_arrive_expect_tx(&full[s], MG_SLOT);
+                                tma_bulk_g2s_hint(ring + s * MG_SLOT, src + static_cast<size_t>(j) * TPS * MG_HD, MG_SLOT, &full[s], pol);
+                            }
+                        }
+                        if (++pg == npg) {
+                            pg = 0;
+                            if (++h == A.H) {
+                                h = 0;
+                                do {
+                                    ++r;
+                                    npg = r < 32 ? s_cum[r + 1] - s_cum[r] : 1;
+                                } while (r < 32 && npg == 0);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ========================================================================================================
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(128, BN);
+        uint32_t it = 0, bit = 0, seg = 0;
+        for (int p = 0; p < A.nph; ++p) {
+            const MegaPhase& P = ph[p];
+            if (P.type != MEGA_GEMM) {
+                it += att_items;
+                continue;
+            }
+            const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
+            int b0, b1;
+            mg_range(T, cta, G, b0, b1);
+            int blk = b0;
+            while (blk < b1) {
+                const int tile = blk / P.kb;
+                const int seg_end = min(b1, (tile + 1) * P.kb);
+                const int stage = seg % MG_NACC;
+                if (seg >= MG_NACC) mg_wait(&accempty[stage], ((seg / MG_NACC) - 1) & 1, A.dbg, 1, p);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + stage * BN;
+                for (bool first = true; blk < seg_end; ++blk, ++it, ++bit, first = false) {
+                    const int s = it % MG_NS, bs = bit % MG_NB;
+                    mg_wait(&full[s], (it / MG_NS) & 1, A.dbg, 1, p);
+                    mg_wait(&bfull[bs], (bit / MG_NB) & 1, A.dbg, 2, p);
+                    tc_fence_after();
+                    if (lane >= 1 && lane < 8) mbar_arrive(&empty[s]);      // 7 of the slot's 8 release arrivals
+                    if (lane == 0) {
+                        const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(ring + s * MG_SLOT));
+                        const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(bring + bs * MG_BSLOT));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                        umma_commit(&empty[s]);                             // the 8th: when these MMAs have read the slot
+                        umma_commit(&bempty[bs]);
+                        if (blk == seg_end - 1) umma_commit(&accfull[stage]);
+                    }
+                    __syncwarp();
+                }
+                ++seg;
+            }
+        }
+    } else if (warp == 2) {
+        // ===== activation (B operand) producer: the only role that waits for the previous phase ===========================
+        if (lane == 0) {
+            uint32_t bit = 0;
+            for (int p = 0; p < A.nph; ++p) {
+                const MegaPhase& P = ph[p];
+                if (P.type != MEGA_GEMM) continue;
+                const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
+                int b0, b1;
+                mg_range(T, cta, G, b0, b1);
+                if (b0 >= b1) continue;
+                if (P.dep_target > 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 3, p);
+                mg_fence_proxy_async();              // other CTAs' generic-proxy stores -> visible to my TMA loads
+                for (int blk = b0; blk < b1; ++blk, ++bit) {
+                    const int tile = blk / P.kb, kbi = blk - tile * P.kb;
+                    const int g = tile / P.tiles_per_group;
+                    const int bs = bit % MG_NB;
+                    if (bit >= MG_NB) mg_wait(&bempty[bs], ((bit / MG_NB) - 1) & 1, A.dbg, 3, p);
+                    mbar_arrive_expect_tx(&bfull[bs], B_BYTES);
+                    tma_load_2d(bring + bs * MG_BSLOT, &A.tmB[P.b_map], &bfull[bs], P.b_col_off + g * P.b_grp_stride + kbi * 64, 0);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== workers: GEMM epilogues / attention ========================================================================
+        const int wtid = threadIdx.x - 128;             // 0..255
+        const int wq = wtid >> 5;                        // worker warp 0..7
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int grp = wq >> 2;                         // which half of the rows in the TMEM read-out
+        uint32_t it = 0, seg = 0, pgc = 0;
+        for (int p = 0; p < A.nph; ++p) {
+            const MegaPhase& P = ph[p];
+            if (P.type == MEGA_GEMM) {
+                const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
+                int b0, b1;
+                mg_range(T, cta, G, b0, b1);
+                const int first_tile = b0 / P.kb;
+                int blk = b0;
+                while (blk < b1) {
+                    const int tile = blk / P.kb;
+                    const int seg_end = min(b1, (tile + 1) * P.kb);
+                    it += seg_end - blk;
+                    blk = seg_end;
+                    const int stage = seg % MG_NACC;
+                    mg_wait(&accfull[stage], (seg / MG_NACC) & 1, A.dbg, 4, p);
+                    tc_fence_after();
+                    ++seg;
+                    // ---- TMEM -> registers: feature = TMEM lane, my group's half of the rows (hi + lo columns) ----------
+                    const uint32_t taddr = tmem_base + stage * BN + (static_cast<uint32_t>(q * 32) << 16);
+                    float v[HB];
+                    {
+                        float hi[16], lo[16];
+                        if constexpr (HB == 16) {
+                            tmem_ld_32x16(taddr + grp * HB, hi);
+                            tmem_ld_32x16(taddr + BPAD + grp * HB, lo);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = hi[j] + lo[j];
+                        } else {
+                            // BPAD = 16: one 16-column load covers both groups' rows; each group keeps its 8
+                            tmem_ld_32x16(taddr, hi);
+                            tmem_ld_32x16(taddr + BPAD, lo);
+#pragma unroll
+                            for (int j = 0; j < HB; ++j) v[j] = grp ? hi[HB + j] + lo[HB + j] : hi[j] + lo[j];
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accempty[stage]);
+                    // ---- my partial of this tile -> workspace [row][feature] ---------------------------------------------------
+                    const int ml = q * 32 + lane;
+                    float* pdst = A.part + (static_cast<size_t>(cta) * MEGA_MAXSEG + (tile - first_tile)) * BPAD * 128 + ml;
+#pragma unroll
+                    for (int j = 0; j < HB; ++j) __stcg(pdst + (grp * HB + j) * 128, v[j]);
+                    __threadfence();
+                    mg_bar_workers();
+                    const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, G);
+                    const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, G);
+                    const int ncontrib = c_last - c_first + 1;
+                    if (wtid == 0) *s_flag = (atomicAdd(A.tile_cnt + p * A.tile_cnt_stride + tile, 1) == ncontrib - 1);
+                    mg_bar_workers();
+                    if (*s_flag) {
+                        __threadfence();
+                        mg_tile_epilogue<BPAD>(A, P, p, tile, c_first, ncontrib, T, G, wq, lane);
+                        __threadfence();
+                        mg_bar_workers();
+                        if (wtid == 0) {
+                            A.tile_cnt[p * A.tile_cnt_stride + tile] = 0;
+                            mg_fence_proxy_async();
+                            __threadfence();
+                            atomicAdd(A.flags + p, 1u);
+                        }
+                    } else {
+                        mg_bar_workers();                 // s_flag is rewritten by the next tile
+                    }
+                }
+            } else {
+                // ===== attention: units [u0, u1) ========================================================================
+                constexpr int LPT = MG_HD / 8, TPW = 32 / LPT, DPT = MG_HD / 32, KPW = MG_PAGE / 8;
+                float* sc_all = reinterpret_cast<float*>(bring + L::A_SC);
+                float* pw = reinterpret_cast<float*>(bring + L::A_PW);
+                float* red = reinterpret_cast<float*>(bring + L::A_RED);
+                if (P.dep_target > 0) {
+                    if (lane == 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 5, p);
+                    __syncwarp();
+                }
+                const int sub = lane % LPT;
+                int r = 0;
+                while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u0) ++r;
+                int npg = s_cum[r + 1] - s_cum[r];
+                int rem = u0 - A.H * s_cum[r];
+                int h = npg ? rem / npg : 0, pg = npg ? rem - h * npg : 0;
+                int u = u0;
+                while (u < u1) {
+                    const int pa = pg, pb = min(npg, pa + (u1 - u));
+                    const int pos = A.row_pos[r];
+                    const bool has_self = pb == npg;                       // the page holding the current position
+                    const int rh = r * A.H + h;
+                    float qv[8], kself[8], vself[DPT];
+                    {
+                        const float4* qp = reinterpret_cast<const float4*>(A.qbuf + static_cast<size_t>(rh) * MG_HD + sub * 8);
+                        const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
+                        qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w;
+                        qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) kself[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < DPT; ++i) vself[i] = 0.f;
+                    if (has_self) {
+                        const float4* kp = reinterpret_cast<const float4*>(A.knew + static_cast<size_t>(rh) * MG_HD + sub * 8);
+                        const float4 k0 = __ldcg(kp), k1 = __ldcg(kp + 1);
+                        kself[0] = k0.x; kself[1] = k0.y; kself[2] = k0.z; kself[3] = k0.w;
+                        kself[4] = k1.x; kself[5] = k1.y; kself[6] = k1.z; kself[7] = k1.w;
+                        const float4 v0 = __ldcg(reinterpret_cast<const float4*>(A.vnew + static_cast<size_t>(rh) * MG_HD + lane * DPT));
+                        vself[0] = v0.x; vself[1] = v0.y; vself[2] = v0.z; vself[3] = v0.w;
+                    }
+                    float m_run = -INFINITY, l_run = 0.f;
+                    float acc[DPT];
+#pragma unroll
+                    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+                    for (int pgi = pa; pgi < pb; ++pgi, ++pgc) {
+                        // ring items of this page: NSL K slots then NSL V slots
+                        uint32_t ks[NSL], vs[NSL];
+#pragma unroll
+                        for (int j = 0; j < NSL; ++j) {
+                            ks[j] = (it + j) % MG_NS;
+                            vs[j] = (it + NSL + j) % MG_NS;
+                        }
+#pragma unroll
+                        for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((it + j) / MG_NS) & 1, A.dbg, 6, p);
+                        float* sc = sc_all + (pgc & 1) * MG_PAGE;
+#pragma unroll
+                        for (int itq = 0; itq < KPW / TPW; ++itq) {
+                            const int t = wq * KPW + itq * TPW + lane / LPT;
+                            const int tg = pgi * MG_PAGE + t;
+                            float kvv[8];
+                            const KVT* Kp = reinterpret_cast<const KVT*>(ring + ks[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + sub * 8;
+                            mg_load_kv<KVT, 8>(Kp, kvv);
+                            if (tg == pos) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) kvv[i] = kself[i];
+                            }
+                            float dsum = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dsum = fmaf(qv[i], kvv[i], dsum);
+#pragma unroll
+                            for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+                            if (sub == 0) sc[t] = (tg <= pos) ? dsum * A.scale : -INFINITY;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[ks[j]]);
+                        }
+                        mg_bar_workers();
+                        const float s0 = sc[lane], s1 = sc[lane + 32];
+                        const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
+                        const float corr = expf(m_run - m_new);
+                        const float e0 = expf(s0 - m_new), e1 = expf(s1 - m_new);
+                        float* mypw = pw + wq * MG_PAGE;
+                        mypw[lane] = e0;
+                        mypw[lane + 32] = e1;
+                        l_run = l_run * corr + warp_sum(e0 + e1);
+                        m_run = m_new;
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((it + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
+#pragma unroll
+                        for (int i = 0; i < DPT; ++i) acc[i] *= corr;
+#pragma unroll
+                        for (int tt = 0; tt < KPW; ++tt) {
+                            const int t = wq * KPW + tt;
+                            const float pt_ = mypw[t];
+                            float vv[DPT];
+                            const KVT* Vp = reinterpret_cast<const KVT*>(ring + vs[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + lane * DPT;
+                            mg_load_kv<KVT, DPT>(Vp, vv);
+                            if (pgi * MG_PAGE + t == pos) {
+#pragma unroll
+                                for (int i = 0; i < DPT; ++i) vv[i] = vself[i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[vs[j]]);
+                        }
+                        it += 2 * NSL;
+                    }
+                    // ---- combine the 8 warps' partial outputs of this item segment -------------------------------------------------
+#pragma unroll
+                    for (int i = 0; i < DPT; ++i) red[wq * MG_HD + lane * DPT + i] = acc[i];
+                    mg_bar_workers();
+                    const size_t ocol = static_cast<size_t>(h) * MG_HD;
+                    if (pa == 0 && pb == npg) {
+                        if (wtid < MG_HD) {
+                            float osum = 0.f;
+#pragma unroll
+                            for (int w = 0; w < 8; ++w) osum += red[w * MG_HD + wtid];
+                            const float o = osum / l_run;
+                            __nv_bfloat16 hi, lo;
+                            split_bf16(o, hi, lo);
+                            A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                            A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                        }
+                        mg_bar_workers();
+                    } else {
+                        // item shared with neighbouring CTAs: publish (o, m, l); the last arriver merges in CTA order
+                        const long long ui0 = static_cast<long long>(A.H) * s_cum[r] + static_cast<long long>(h) * npg;
+                        const int c_first = mg_owner(ui0, U, G), c_last = mg_owner(ui0 + npg - 1, U, G);
+                        const int nch = c_last - c_first + 1;
+                        float* base = A.att_ws + static_cast<size_t>(rh) * MEGA_ATT_MAXC * (MG_HD + 2);
+                        float* myws = base + static_cast<size_t>(cta - c_first) * (MG_HD + 2);
+                        if (wtid < MG_HD) {
+                            float osum = 0.f;
+#pragma unroll
+                            for (int w = 0; w < 8; ++w) osum += red[w * MG_HD + wtid];
+                            __stcg(myws + wtid, osum);
+                        }
+                        if (wtid == 0) {
+                            __stcg(myws + MG_HD, m_run);
+                            __stcg(myws + MG_HD + 1, l_run);
+                        }
+                        __threadfence();
+                        mg_bar_workers();
+                        if (wtid == 0) *s_flag = (atomicAdd(A.att_cnt + rh, 1) == nch - 1);
+                        mg_bar_workers();
+                        if (*s_flag) {
+                            __threadfence();
+                            if (wtid < MG_HD) {
+                                float M = -INFINITY;
+                                for (int c = 0; c < nch; ++c) M = fmaxf(M, __ldcg(base + c * (MG_HD + 2) + MG_HD));
+                                float Lsum = 0.f, O = 0.f;
+                                for (int c = 0; c < nch; ++c) {
+                                    const float w = expf(__ldcg(base + c * (MG_HD + 2) + MG_HD) - M);
+                                    Lsum += __ldcg(base + c * (MG_HD + 2) + MG_HD + 1) * w;
+                                    O += __ldcg(base + c * (MG_HD + 2) + wtid) * w;
+                                }
+                                const float o = O / Lsum;
+                                __nv_bfloat16 hi, lo;
+                                split_bf16(o, hi, lo);
+                                A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                                A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                            }
+                            if (wtid == 0) A.att_cnt[rh] = 0;
+                        }
+                        mg_bar_workers();
+                    }
+                    // ---- next item ----------------------------------------------------------------------------------------------------
+                    u += pb - pa;
+                    pg = pb;
+                    if (pg == npg) {
+                        pg = 0;
+                        if (++h == A.H) {
+                            h = 0;
+                            do {
+                                ++r;
+                                npg = r < 32 ? s_cum[r + 1] - s_cum[r] : 1;
+                            } while (r < 32 && npg == 0);
+                        }
+                    }
+                }
+                // this CTA's share of the phase is done (merged outputs are counted by whoever merged them)
+                __threadfence();
+                mg_bar_workers();
+                if (wtid == 0) {
+                    mg_fence_proxy_async();
+                    __threadfence();
+                    atomicAdd(A.flags + p, 1u);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------------
+template <int BPAD, typename KVT>
+static int mega_launch_t(const MegaArgs& a, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VCB_CUDA_OK(cudaFuncSetAttribute(mega_step_kernel<BPAD, KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MegaSmem::TOTAL));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(MG_THREADS);
+    cfg.dynamicSmemBytes = MegaSmem::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;       // every CTA must be co-resident: the phase hand-over spins on peers
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, mega_step_kernel<BPAD, KVT>, a));
+    return 0;
+}
+
+int mega_launch(const MegaArgs& a, int grid, cudaStream_t st) {
+    if (a.bpad == 32) return a.kv_fp32 ? mega_launch_t<32, float>(a, grid, st) : mega_launch_t<32, __nv_bfloat16>(a, grid, st);
+    if (a.bpad == 16) return a.kv_fp32 ? mega_launch_t<16, float>(a, grid, st) : mega_launch_t<16, __nv_bfloat16>(a, grid, st);
+    set_error("mega_launch: unsupported bpad %d", a.bpad);
+    return -1;
+}
+
+// co-resident CTAs the device offers this kernel (one per SM: the ring takes the whole shared memory)
+int mega_max_grid(int bpad, int kv_fp32) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cudaError_t e;
+    auto occ = [&](auto kern) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MegaSmem::TOTAL);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MG_THREADS, MegaSmem::TOTAL);
+    };
+    if (bpad == 32) kv_fp32 ? occ(mega_step_kernel<32, float>) : occ(mega_step_kernel<32, __nv_bfloat16>);
+    else kv_fp32 ? occ(mega_step_kernel<16, float>) : occ(mega_step_kernel<16, __nv_bfloat16>);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return sms * std::min(per_sm, 1);
+}
+
+size_t mega_part_floats(int grid, int bpad) { return static_cast<size_t>(grid) * MEGA_MAXSEG * bpad * 128; }
+
+}  // namespace vcb

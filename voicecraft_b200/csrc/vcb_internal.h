@@ -42,6 +42,10 @@ struct GemmEpilogue {
     const float* next_gamma = nullptr;
     __nv_bfloat16* next_act = nullptr;
     float* stats_out = nullptr;
+    // EPI_QKV, persistent step kernel only: the new token's k / v (rounded like the cache) as fp32 rows [rows, d] -- the
+    // attention phase takes the current position from here, so its K/V page stream never depends on this step's GEMM
+    float* knew = nullptr;
+    float* vnew = nullptr;
 };
 static constexpr int STATS_ROWS = 128;
 
@@ -61,6 +65,51 @@ struct ChainArgs {
 };
 int chain_launch(const ChainArgs& args, int bpad, int nclusters, int pdl, cudaStream_t st);
 int chain_max_clusters(int bpad);
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent decode-step kernel (mega_step.cu): one launch runs every layer of a decode step.
+// ---------------------------------------------------------------------------------------------------
+enum { MEGA_GEMM = 0, MEGA_ATTN = 1 };
+static constexpr int MEGA_MAXSEG = 8;          // output tiles a CTA's block range may touch in one GEMM phase
+static constexpr int MEGA_ATT_MAXC = 16;       // CTAs that may share one (row, head) attention item
+struct MegaPhase {
+    int type = MEGA_GEMM;
+    // GEMM: `groups` matrices of tiles_per_group x kb 16 KB weight blocks (groups > 1: the K second-stage logit heads)
+    int groups = 1, tiles_per_group = 0, kb = 0, Nout = 0;
+    int b_map = 0, b_col_off = 0, b_grp_stride = 0, col_grp_stride = 0;
+    const CUtensorMap* tmA = nullptr;         // device array [groups]
+    const float* const* grp_bias = nullptr;   // device array [groups] or null (ep.bias)
+    GemmEpilogue ep;
+    // ATTN: this layer's pools
+    const void* kpool = nullptr;
+    const void* vpool = nullptr;
+    int dep_target = 0;                       // completions of the previous phase this one waits for (0: none)
+    int done_target = 0;                      // completions that finish this phase (tiles, or CTAs for ATTN)
+};
+struct MegaArgs {
+    CUtensorMap tmB[4];                 // activation operands: 0 act_d, 1 act_d2, 2 act_f, 3 act_h
+    const MegaPhase* ph = nullptr;      // device array
+    int nph = 0, nvalid = 0, bpad = 0, kv_fp32 = 0;
+    unsigned int* flags = nullptr;      // [nph] completion counters (zeroed by step_prep)
+    int* tile_cnt = nullptr;            // [nph][max tiles] split-K arrival counters (self-resetting)
+    int tile_cnt_stride = 0;
+    float* part = nullptr;              // [grid][MEGA_MAXSEG][bpad][128] split-K partials
+    unsigned int* dbg = nullptr;        // watchdog record
+    // attention
+    const float* qbuf = nullptr;
+    const float* knew = nullptr;
+    const float* vnew = nullptr;
+    __nv_bfloat16* att_out = nullptr;   // act_d (hi/lo rows)
+    float* att_ws = nullptr;            // [rows*H][MEGA_ATT_MAXC][hd+2]
+    int* att_cnt = nullptr;             // [nph? no: rows*H] arrival counters (self-resetting)
+    const int* row_pos = nullptr;
+    const int* row_pages = nullptr;
+    int max_pages = 0, H = 0, d = 0;
+    float scale = 0.f;
+};
+int mega_launch(const MegaArgs& a, int grid, cudaStream_t st);
+int mega_max_grid(int bpad, int kv_fp32);
+size_t mega_part_floats(int grid, int bpad);
 
 // Grouped launch of gemm_w_xT_cluster (blockIdx.y = group): weight tensor maps in a device array, per-group bias pointers.
 struct GemmGroup {
@@ -134,11 +183,15 @@ struct GroupState {
     int arrive;         // scratch: member slots finished in this step
     int n_spans_done;
     int first_slot;     // slot id of member 0 (members are consecutive slots)
-    int pad0;
+    // Device-side sampling noise (sampler_kernel, noise pointer null): the Philox4x32-10 stream torch's CUDA generator
+    // would hand to `torch.multinomial` for a draw of shape [size*K, V] (ATen distribution_nullary_kernel + exponential_):
+    // rng_threads = 256 * grid of that launch (0: this group needs caller-provided noise), offset advances per sampling step.
+    unsigned int rng_threads;
     int more_mask[8];   // edit mode: mask_embedding rows of the spans still to come
     int span_ends[8];   // n_steps at which each span finished
-    int pad[4];
+    unsigned int seed_lo, seed_hi, off_lo, off_hi;
 };
+static_assert(sizeof(GroupState) == 128, "GroupState is copied in bulk by vcb_poll");
 
 struct SamplingParams {
     int top_k;

@@ -25,16 +25,32 @@ def partition(lengths: Sequence[int], world_size: int, rank: int) -> List[int]:
     return [i for i in range(len(lengths)) if owner[i] == rank]
 
 
-def gather_token_lists(local: List[torch.Tensor], local_ids: List[int], n_total: int, group=None) -> List[torch.Tensor]:
+def _exchange_device(local, group, device):
+    """Device the collective runs on: NCCL needs CUDA tensors on EVERY rank, including one that decoded nothing
+    (partition() leaves ranks empty when there are fewer utterances than ranks)."""
+    if device is not None:
+        return torch.device(device)
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return local[0].device if local else torch.device("cpu")
+
+
+last_gather_bytes = 0       # bytes this rank contributed to the last gather_token_lists (bench.py reports it)
+
+
+def gather_token_lists(local: List[torch.Tensor], local_ids: List[int], n_total: int, group=None, device=None) -> List[torch.Tensor]:
     """All ranks end up with the full list (indexed by global utterance id) of [K, T_i] int64 token matrices.
-    Works on CPU tensors with gloo and CUDA tensors with NCCL."""
+    Works on CPU tensors with gloo and CUDA tensors with NCCL; a rank may hold no utterance at all."""
+    global last_gather_bytes
+    last_gather_bytes = 0
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         out = [None] * n_total
         for i, t in zip(local_ids, local):
             out[i] = t
         return out
     world = dist.get_world_size(group)
-    dev = local[0].device if local else torch.device("cpu")
+    dev = _exchange_device(local, group, device)
+    local = [t.to(dev) for t in local]
     K = local[0].shape[0] if local else 0
     meta = torch.tensor([len(local), K, max((t.shape[1] for t in local), default=0)], dtype=torch.int64, device=dev)
     metas = [torch.zeros_like(meta) for _ in range(world)]
@@ -51,6 +67,7 @@ def gather_token_lists(local: List[torch.Tensor], local_ids: List[int], n_total:
     infos = [torch.empty_like(info) for _ in range(world)]
     dist.all_gather(packs, pack, group=group)
     dist.all_gather(infos, info, group=group)
+    last_gather_bytes = (pack.numel() + info.numel() + meta.numel()) * 8
     out = [None] * n_total
     for p, inf in zip(packs, infos):
         for j in range(n_max):

@@ -9,9 +9,12 @@ without a Blackwell GPU the calls raise.
 
 Random numbers: the reference samples with ``torch.multinomial(softmax(l), 1)``, which ATen evaluates as
 ``argmax(softmax(l) / q)`` with ``q = empty_like(p).exponential_(1)`` from the device's global generator.
-This module draws exactly that ``q`` (same shape, once per sampling step) on the model's device and hands
-it to the fused sampler kernel, so the generator state advances as in the reference.  ``noise_fn`` can
-replace the draw (tests feed CPU-generator noise to compare against the CPU oracle).
+The fused sampler kernel generates exactly that ``q`` itself: every utterance (or best-of-N group) owns the
+Philox stream of a torch CUDA generator at (seed, offset) and consumes, per sampling step, what the reference's
+draw of shape ``[n*K, V]`` consumes.  ``inference_tts`` / ``inference_tts_batch`` / ``inference`` take the
+stream of the model device's default generator and leave it advanced as the reference would; batched sessions
+give every utterance its own seed, so row *i* of a batch equals the single call of utterance *i* under that
+seed.  ``noise_fn`` replaces the generator (tests feed CPU-generator noise to compare with the CPU oracle).
 
 Out of scope (training): ``forward`` and ``prepare_mask_intervals`` raise NotImplementedError.
 """
@@ -98,44 +101,6 @@ class _Decoder(nn.Module):
         self.norm = nn.LayerNorm(d, eps=1e-5)
 
 
-class _NoiseRing:
-    """Exp(1) draws for the fused sampler, generated on a side stream.
-
-    The draw for step i does not depend on step i-1, but as a kernel on the decode stream it sits between the sampler of
-    step i-1 and the first kernel of step i (two grid drains + ~5 us every step).  Here the same ``exponential_`` calls
-    are issued in the same host order (the generator state advances exactly as before) on a second stream into a small
-    ring of buffers; events order producer -> consumer (ready) and consumer -> producer (buffer reuse)."""
-
-    def __init__(self, shape, device, depth=4):
-        self.bufs = [torch.empty(shape, device=device, dtype=torch.float32) for _ in range(depth)]
-        self.side = torch.cuda.Stream(device=device)
-        for b in self.bufs:
-            b.record_stream(self.side)
-        self.ready = [torch.cuda.Event() for _ in range(depth)]
-        self.freed = [None] * depth
-        self.i = 0
-        # the buffers were allocated on the current stream
-        self.side.wait_stream(torch.cuda.current_stream(device))
-
-    def draw(self):
-        """enqueue one draw; returns (buffer, token): the current stream waits for it, call consumed(token) after the
-        launch that reads it"""
-        j = self.i % len(self.bufs)
-        self.i += 1
-        if self.freed[j] is not None:
-            self.side.wait_event(self.freed[j])
-        with torch.cuda.stream(self.side):
-            self.bufs[j].exponential_(1)
-            self.ready[j].record(self.side)
-        torch.cuda.current_stream(self.bufs[j].device).wait_event(self.ready[j])
-        return self.bufs[j], j
-
-    def consumed(self, j):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.bufs[j].device))
-        self.freed[j] = ev
-
-
 class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
     def __new__(cls, args: Optional[Namespace] = None, config: Optional[Dict] = None, **kwargs):
         if args is not None:
@@ -189,8 +154,8 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         self._eng_key = None
         self._eng_opts = dict(max_slots=8, max_seq_len=2048, max_new_tokens=4096, kv_dtype="bf16")
         self.noise_fn = None          # optional: callable(shape, device) -> fp32 Exp(1) tensor on `device`
-        self.side_stream_noise = os.environ.get("VCB_SIDE_NOISE", "1") != "0"
         self.poll_every = 4           # inference_tts*: poll the done flag every N steps (device generator only)
+        self._sessions = set()        # open DecodeSessions (they hold engine slots; the engine is not rebuilt under them)
         self.last_stats = {}
         self.trace_logits = None      # set to a list to collect the raw logits [n*K, V] of every sampling step
 
@@ -217,12 +182,29 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
 
     def _drop_engine(self):
         if getattr(self, "_eng", None) is not None:
+            live = [s for s in getattr(self, "_sessions", ()) if s._open]
+            if live:
+                raise _lib.VcbError(f"{len(live)} DecodeSession(s) still hold slots of this engine: close them before "
+                                    "reconfiguring / moving / reloading the model")
             _lib.load().vcb_destroy(self._eng)
         self._eng = None
         self._eng_key = None
 
+    def _free_slots(self, n, eng_slots):
+        """first of n consecutive engine slots not held by an open session (single calls and sessions share one engine)"""
+        used = set()
+        for s in self._sessions:
+            if s._open:
+                used.update(s.slots)
+        for base in range(0, eng_slots - n + 1):
+            if not any((base + i) in used for i in range(n)):
+                return base
+        raise _lib.VcbError("no free engine slots")
+
     def __del__(self):
         try:
+            for sess in list(getattr(self, "_sessions", ())):
+                sess.close()
             self._drop_engine()
         except Exception:
             pass
@@ -244,7 +226,12 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         if dev.type != "cuda":
             raise _lib.VcbError("VoiceCraft (B200) has no CPU path: move the model to a CUDA device (`.to('cuda')`)")
         o = self._eng_opts
+        held = sum(len(s.slots) for s in self._sessions if s._open)
+        need_slots += held
         if need_slots > o["max_slots"] or need_seq > o["max_seq_len"]:
+            if held:
+                raise _lib.VcbError(f"engine too small (max_slots={o['max_slots']}, max_seq_len={o['max_seq_len']}) and "
+                                    f"{held} slot(s) are held by open DecodeSessions: close them or configure_engine() first")
             o["max_slots"] = max(o["max_slots"], need_slots)
             o["max_seq_len"] = max(o["max_seq_len"], (need_seq + 255) // 256 * 256)
             self._drop_engine()
@@ -290,25 +277,24 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             sp.silence_tokens[i] = int(t)
         return sp
 
-    def _noise_source(self, shape, device):
-        """returns draw() -> (tensor, done_callback): device-generator draws come from a side-stream ring, custom
-        ``noise_fn`` draws from one persistent buffer on the decode stream"""
-        if self.noise_fn is None and self.side_stream_noise:
-            ring = _NoiseRing(shape, device)
-            def draw():
-                buf, tok = ring.draw()
-                return buf, (lambda: ring.consumed(tok))
-            return draw
-        buf = torch.empty(shape, device=device, dtype=torch.float32)
-        return lambda: (self._draw_noise(buf), (lambda: None))
+    @staticmethod
+    def _rng_threads(dev, numel):
+        """threads of ATen's distribution_nullary_kernel for a draw of `numel` elements (calc_execution_policy)"""
+        p = torch.cuda.get_device_properties(dev)
+        grid = min((numel + 255) // 256, p.multi_processor_count * (p.max_threads_per_multi_processor // 256))
+        return 256 * grid
+
+    def _check_ids(self, x_ids, y_tok):
+        """the reference raises on an out-of-range id (nn.Embedding / F.embedding); the kernels index raw tables"""
+        if x_ids.numel() and (int(x_ids.min()) < 0 or int(x_ids.max()) >= self.n_text_tokens):
+            raise IndexError(f"text id out of range [0, {self.n_text_tokens})")
+        if y_tok.numel() and (int(y_tok.min()) < 0 or int(y_tok.max()) >= self.n_audio_tokens[0]):
+            raise IndexError(f"audio token out of range [0, {self.n_audio_tokens[0]})")
 
     def _draw_noise(self, buf):
-        """Exp(1) noise with the call shape of the reference's multinomial draw (in place on a persistent buffer)."""
-        if self.noise_fn is not None:
-            q = self.noise_fn(tuple(buf.shape), buf.device)
-            buf.copy_(q.to(device=buf.device, dtype=torch.float32))
-        else:
-            buf.exponential_(1)
+        """caller-provided Exp(1) noise with the call shape of the reference's multinomial draw"""
+        q = self.noise_fn(tuple(buf.shape), buf.device)
+        buf.copy_(q.to(device=buf.device, dtype=torch.float32))
         return buf
 
     def shift(self, rearranged_y):
@@ -325,29 +311,26 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
     def _run(self, eng, slots, n_rows, sp, stream, max_steps=None, speculative=False):
         """prefill is done; run sample / decode_step until every listed slot's group is done.
 
-        speculative (TTS with the device generator only): poll every `poll_every` steps instead of every step.  Steps
-        issued after the group finished are no-ops on the device, but each consumed one [n*K,V] draw of the generator;
-        the surplus is handed back by rewinding the Philox offset, so the generator ends exactly where the reference's would."""
+        Device generator (noise_fn is None): the sampler draws from the group's own Philox stream; a finished group
+        ignores further steps and consumes nothing, so the done flag is polled only every `poll_every` steps
+        (speculative, TTS) and the generator still ends exactly where the reference's would."""
         lib = _lib.load()
         a = self.args
         dev = self.mask_embedding.device
         K, V = a.n_codebooks, self.n_audio_tokens[0]
         n = len(slots)
         c_slots = (C.c_int32 * n)(*slots)
-        draw = self._noise_source((n_rows * K, V), dev)
+        host_noise = self.noise_fn is not None
+        buf = torch.empty((n_rows * K, V), device=dev, dtype=torch.float32) if host_noise else None
         status = (_lib.vcb_status * n)()
         def trace():
             if self.trace_logits is not None:
                 t = torch.empty(n_rows * K, V, device=dev, dtype=torch.float32)
                 _lib.check(lib.vcb_debug_logits(eng, t.data_ptr(), n_rows * K))
                 self.trace_logits.append(t)
-        every = max(1, int(self.poll_every)) if (speculative and self.noise_fn is None and self.trace_logits is None) else 1
-        gen = torch.cuda.default_generators[dev.index or 0] if every > 1 else None
-        off0 = gen.get_offset() if gen is not None else 0
-        noise, used_up = draw()
-        delta = (gen.get_offset() - off0) if gen is not None else 0      # generator advance per draw of this shape
-        _lib.check(lib.vcb_sample(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
-        used_up()
+        every = max(1, int(self.poll_every)) if (speculative and not host_noise and self.trace_logits is None) else 1
+        noise = self._draw_noise(buf).data_ptr() if host_noise else None
+        _lib.check(lib.vcb_sample(eng, c_slots, n, noise, C.byref(sp), stream))
         trace()
         steps = 1
         while True:
@@ -361,17 +344,23 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             if max_steps is not None and steps >= max_steps:
                 break
             forced = every == 1 and any(s.forced for s in status)
-            if not forced:                               # forced hand-over steps consume no random numbers
-                noise, used_up = draw()
-            _lib.check(lib.vcb_decode_step(eng, c_slots, n, noise.data_ptr(), C.byref(sp), stream))
+            if host_noise and not forced:                # forced hand-over steps consume no random numbers
+                noise = self._draw_noise(buf).data_ptr()
+            _lib.check(lib.vcb_decode_step(eng, c_slots, n, noise, C.byref(sp), stream))
             if not forced:
-                used_up()
                 trace()
             steps += 1
-        if gen is not None and delta > 0:
-            used = max(int(s.n_steps) for s in status)                # sampling steps the reference would have drawn for
-            gen.set_offset(off0 + used * delta)
         return status
+
+    def _device_rng(self, P, dev, n_rows):
+        """hand the model device's default generator stream to the prompt (no-op with a caller noise_fn)"""
+        if self.noise_fn is not None:
+            return None
+        gen = torch.cuda.default_generators[dev.index or 0]
+        P.rng_seed = int(gen.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        P.rng_offset = int(gen.get_offset())
+        P.rng_threads = self._rng_threads(dev, n_rows * self.args.n_codebooks * self.n_audio_tokens[0])
+        return gen
 
     def _read_rows(self, eng, slot, n_steps, stream):
         K = self.args.n_codebooks
@@ -426,19 +415,24 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         eng = self._engine(need_slots=n_copies, need_seq=need_seq)
         lib = _lib.load()
         x_ids = x[0].long().contiguous()
+        self._check_ids(x_ids, y_tok)
         sp = self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
-            P = _lib.vcb_prompt(slot=0, n_copies=n_copies, mode=0, x_len=x_len, text_ids_dev=x_ids.data_ptr(),
+            base = self._free_slots(n_copies, self._eng_opts["max_slots"])
+            P = _lib.vcb_prompt(slot=base, n_copies=n_copies, mode=0, x_len=x_len, text_ids_dev=x_ids.data_ptr(),
                                 y_len=y_len, y_tokens_dev=y_tok.data_ptr(), mask_rows_dev=None, n_more_spans=0)
+            gen_state = self._device_rng(P, dev, n_copies)
+            _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))      # a failed prefill holds nothing
             try:
-                _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))
-                slots = list(range(n_copies))
+                slots = [base + i for i in range(n_copies)]
                 status = self._run(eng, slots, n_copies, sp, stream, speculative=True)
                 keep = status[0].keep if n_copies > 1 else 0
-                rows = self._read_rows(eng, keep, status[keep].n_steps, stream)
+                rows = self._read_rows(eng, base + keep, status[keep].n_steps, stream)
+                if gen_state is not None:
+                    gen_state.set_offset(int(status[0].rng_offset))
             finally:
-                lib.vcb_release(eng, 0, n_copies)
+                lib.vcb_release(eng, base, n_copies)
         gen = torch.from_numpy(self._undelay(rows, K)).to(dev)
         res = torch.cat([y[0].long(), gen], dim=1).unsqueeze(0)
         expected = y.shape[2] + rows.shape[0] - K
@@ -523,6 +517,8 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         assert y.shape[0] == 1 and y.shape[1] == K, y.shape
         assert mask_interval.shape == torch.Size((1, mask_interval.shape[1], 2)), mask_interval
         spans = [(int(s), int(e)) for s, e in mask_interval[0].tolist()]
+        if len(spans) > min(8, int(a.max_n_spans)):
+            raise ValueError(f"{len(spans)} masked spans: at most min(8, max_n_spans={a.max_n_spans}) per utterance")
         logging.info(f"silence tokens: {silence_tokens}, note that if you are not using the pretrained encodec "
                      f"6f79c6a8, make sure you specified it yourself, rather than using the default")
         y0 = y[0].long().contiguous()
@@ -533,21 +529,26 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
         eng = self._engine(need_slots=1, need_seq=need_seq)
         lib = _lib.load()
         x_ids = x[0].long().contiguous()
+        self._check_ids(x_ids, y_tok)
         sp = self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
-            P = _lib.vcb_prompt(slot=0, n_copies=1, mode=1, x_len=x_len, text_ids_dev=x_ids.data_ptr(), y_len=y_len,
+            base = self._free_slots(1, self._eng_opts["max_slots"])
+            P = _lib.vcb_prompt(slot=base, n_copies=1, mode=1, x_len=x_len, text_ids_dev=x_ids.data_ptr(), y_len=y_len,
                                 y_tokens_dev=y_tok.data_ptr(), mask_rows_dev=mask_rows.data_ptr(),
                                 n_more_spans=len(more_vals))
             for i, v in enumerate(more_vals):
                 P.more_mask_rows[i] = int(v)
+            gen_state = self._device_rng(P, dev, 1)
+            _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))      # a failed prefill holds nothing
             try:
-                _lib.check(lib.vcb_prefill(eng, C.byref(P), 1, stream))
-                status = self._run(eng, [0], 1, sp, stream)
-                rows = self._read_rows(eng, 0, status[0].n_steps, stream)
+                status = self._run(eng, [base], 1, sp, stream)
+                rows = self._read_rows(eng, base, status[0].n_steps, stream)
                 ends = [status[0].span_ends[i] for i in range(status[0].n_spans_done)]
+                if gen_state is not None:
+                    gen_state.set_offset(int(status[0].rng_offset))
             finally:
-                lib.vcb_release(eng, 0, 1)
+                lib.vcb_release(eng, base, 1)
         assert len(ends) == len(spans), f"len(generated): {len(ends)}, num_mask: {len(spans)}"
         pieces, lo = [], 0
         for (s0, s1), hi in zip(non_mask, ends):
@@ -567,11 +568,11 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
     # state machine; one Exp(1) draw of shape [B*K, V] per step feeds all of them.
     # ------------------------------------------------------------------------------------------------
     def open_edit_session(self, xs, ys, mask_intervals, top_k=-100, top_p=1.0, temperature=1.0, stop_repetition=-1,
-                          silence_tokens=(1388, 1898, 131)):
+                          silence_tokens=(1388, 1898, 131), seeds=None, noise_fns=None):
         """Independent speech-editing utterances decoded as one batch (BASELINE config 3).  mask_intervals: list of
         [1,M,2] tensors.  Returns a DecodeSession; results() gives the edited [1,K,T'] per utterance."""
         return DecodeSession(self, xs, ys, self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens),
-                             mask_intervals=mask_intervals)
+                             mask_intervals=mask_intervals, seeds=seeds, noise_fns=noise_fns)
 
     @torch.no_grad()
     def inference_many(self, xs, ys, mask_intervals, poll_every: int = 4, **kw):
@@ -588,10 +589,16 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
             sess.close()
 
     def open_tts_session(self, xs, ys, top_k=-100, top_p=1.0, temperature=1.0, stop_repetition=3,
-                         silence_tokens=(1388, 1898, 131)):
+                         silence_tokens=(1388, 1898, 131), seeds=None, noise_fns=None):
         """xs: list of [1,L] int64, ys: list of [1,T,K] int64 (any device).  Prefills every utterance (one packed,
-        chunked pass) and returns a DecodeSession whose .step() runs one decode step for all of them."""
-        return DecodeSession(self, xs, ys, self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens))
+        chunked pass) and returns a DecodeSession whose .step() runs one decode step for all of them.
+
+        seeds: one generator seed per utterance -- utterance i samples from the Philox stream of a torch CUDA generator
+        seeded with seeds[i] (offset 0), i.e. its tokens equal ``torch.manual_seed(seeds[i]); inference_tts(x_i, ., y_i)``.
+        Default: the device generator's current seed + i at its current offset (the global generator is left untouched).
+        noise_fns: instead, one callable(shape=[K,V], device) per utterance (tests: CPU-generator noise for the oracle)."""
+        return DecodeSession(self, xs, ys, self._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens),
+                             seeds=seeds, noise_fns=noise_fns)
 
     @torch.no_grad()
     def inference_tts_many(self, xs, ys, poll_every: int = 8, **kw):
@@ -609,9 +616,9 @@ class VoiceCraft(nn.Module, *_HubBase, **_HUB_KW):
 
 
 class DecodeSession:
-    """A batch of independent TTS utterances resident in the engine (slots 0..B-1)."""
+    """A batch of independent utterances resident in the engine, one slot and one random stream each."""
 
-    def __init__(self, model: "VoiceCraft", xs, ys, sp, mask_intervals=None):
+    def __init__(self, model: "VoiceCraft", xs, ys, sp, mask_intervals=None, seeds=None, noise_fns=None):
         a = model.args
         self.edit = mask_intervals is not None
         self.non_mask = []
@@ -620,8 +627,14 @@ class DecodeSession:
         self.model, self.sp, self.dev, self.K = model, sp, dev, K
         self.B = len(xs)
         self.lib = _lib.load()
+        self._open = False
+        self.slots = []
         prompts, keep_alive, need_seq = [], [], 0
         self.y0 = []
+        if seeds is not None and len(seeds) != self.B:
+            raise ValueError("seeds: one per utterance")
+        if noise_fns is not None and len(noise_fns) != self.B:
+            raise ValueError("noise_fns: one per utterance")
         for x, y in zip(xs, ys):
             assert x.ndim == 2 and y.ndim == 3 and y.shape[2] == K
             x = x.to(dev, non_blocking=True)
@@ -632,6 +645,8 @@ class DecodeSession:
             idx = len(prompts)
             if self.edit:
                 spans = [(int(s), int(e)) for s, e in mask_intervals[idx][0].tolist()]
+                if len(spans) > min(8, int(a.max_n_spans)):
+                    raise ValueError(f"{len(spans)} masked spans: at most min(8, max_n_spans={a.max_n_spans}) per utterance")
                 y_tok, mask_rows, more_vals, non_mask = model._edit_prompt(yk, spans)
                 self.non_mask.append(non_mask)
                 cap = int(x.shape[1]) * 10
@@ -648,39 +663,62 @@ class DecodeSession:
             self.y0.append(yk)
             need_seq = max(need_seq, int(x.shape[1]) + max(int(y_tok.shape[0]), cap + 1) + extra + 8)
             prompts.append((int(x.shape[1]), x_ids, int(y_tok.shape[0]), y_tok, mask_rows, more_vals))
+        # one range check for the whole batch (the reference's embedding lookups raise on a bad id)
+        model._check_ids(torch.cat([p[1] for p in prompts]), torch.cat([p[3].reshape(-1) for p in prompts]))
         self.eng = model._engine(need_slots=self.B, need_seq=need_seq)
         self.V = model.n_audio_tokens[0]
+        base = model._free_slots(self.B, model._eng_opts["max_slots"])
+        slots = [base + i for i in range(self.B)]
+        # random streams: caller noise (model.noise_fn: one [B*K,V] draw per step; noise_fns: one [K,V] draw per utterance
+        # and step) or, by default, one Philox stream per utterance generated inside the sampler kernel
+        self._noise_fns = noise_fns
+        self._host_noise = noise_fns is not None or model.noise_fn is not None
+        self._buf = torch.empty((self.B * K, self.V), device=dev, dtype=torch.float32) if self._host_noise else None
+        gen = torch.cuda.default_generators[dev.index or 0]
+        seed0, off0 = int(gen.initial_seed()), int(gen.get_offset())
+        threads = model._rng_threads(dev, K * self.V)
         P = (_lib.vcb_prompt * self.B)()
         for i, (xl, x_ids, yl, y_tok, mask_rows, more_vals) in enumerate(prompts):
-            P[i] = _lib.vcb_prompt(slot=i, n_copies=1, mode=1 if self.edit else 0, x_len=xl, text_ids_dev=x_ids.data_ptr(),
+            P[i] = _lib.vcb_prompt(slot=slots[i], n_copies=1, mode=1 if self.edit else 0, x_len=xl, text_ids_dev=x_ids.data_ptr(),
                                    y_len=yl, y_tokens_dev=y_tok.data_ptr(),
                                    mask_rows_dev=mask_rows.data_ptr() if mask_rows is not None else None,
                                    n_more_spans=len(more_vals))
             for j, v in enumerate(more_vals):
                 P[i].more_mask_rows[j] = int(v)
-        self.c_slots = (C.c_int32 * self.B)(*range(self.B))
+            if not self._host_noise:
+                P[i].rng_seed = (int(seeds[i]) if seeds is not None else seed0 + i) & 0xFFFFFFFFFFFFFFFF
+                P[i].rng_offset = 0 if seeds is not None else off0
+                P[i].rng_threads = threads
+        self.c_slots = (C.c_int32 * self.B)(*slots)
         self.status = (_lib.vcb_status * self.B)()
-        self._draw = model._noise_source((self.B * K, self.V), dev)
         self.steps = 0
-        self._open = True
         with torch.cuda.device(dev):
             self.stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(self.lib.vcb_prefill(self.eng, P, self.B, self.stream))
+            _lib.check(self.lib.vcb_prefill(self.eng, P, self.B, self.stream))     # a failed prefill holds nothing
+        self.slots = slots
+        self._open = True
+        model._sessions.add(self)
         self._keep_alive = keep_alive
+
+    def _noise(self):
+        if not self._host_noise:
+            return None
+        if self._noise_fns is not None:
+            K = self.K
+            for i, fn in enumerate(self._noise_fns):
+                self._buf[i * K:(i + 1) * K].copy_(fn((K, self.V), self.dev).to(device=self.dev, dtype=torch.float32))
+        else:
+            self.model._draw_noise(self._buf)
+        return self._buf.data_ptr()
 
     def sample(self):
         """first sampling step (on the prefill's last hidden states)"""
-        noise, used_up = self._draw()
-        _lib.check(self.lib.vcb_sample(self.eng, self.c_slots, self.B, noise.data_ptr(), C.byref(self.sp), self.stream))
-        used_up()
+        _lib.check(self.lib.vcb_sample(self.eng, self.c_slots, self.B, self._noise(), C.byref(self.sp), self.stream))
         self.steps += 1
 
     def step(self):
-        # edit sessions: forced hand-over steps of individual utterances simply ignore their noise rows
-        noise, used_up = self._draw()
-        _lib.check(self.lib.vcb_decode_step(self.eng, self.c_slots, self.B, noise.data_ptr(), C.byref(self.sp),
-                                            self.stream))
-        used_up()
+        # edit sessions: forced hand-over steps of individual utterances ignore their noise rows / consume no draw
+        _lib.check(self.lib.vcb_decode_step(self.eng, self.c_slots, self.B, self._noise(), C.byref(self.sp), self.stream))
         self.steps += 1
 
     def poll(self):
@@ -697,14 +735,14 @@ class DecodeSession:
     def raw_tokens(self, i):
         """delayed token rows [n_steps, K] of utterance i (host numpy)"""
         st = self.poll()
-        return self.model._read_rows(self.eng, i, st[i].n_steps, self.stream)
+        return self.model._read_rows(self.eng, self.slots[i], st[i].n_steps, self.stream)
 
     def results(self):
         out = []
         a = self.model.args
         st = self.poll()
         for i in range(self.B):
-            rows = self.model._read_rows(self.eng, i, st[i].n_steps, self.stream)
+            rows = self.model._read_rows(self.eng, self.slots[i], st[i].n_steps, self.stream)
             if self.edit:
                 assert st[i].done, "edit session results() needs finished utterances"
                 ends = [st[i].span_ends[j] for j in range(st[i].n_spans_done)]
@@ -733,6 +771,7 @@ class DecodeSession:
 
     def close(self):
         if self._open:
-            for i in range(self.B):
-                self.lib.vcb_release(self.eng, i, 1)
+            for s in self.slots:
+                self.lib.vcb_release(self.eng, s, 1)
             self._open = False
+        self.model._sessions.discard(self)
