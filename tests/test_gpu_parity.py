@@ -425,3 +425,51 @@ def test_headline_830M_reference_pinned_utterance(j):
     m.noise_fn = gu.cpu_noise_fn(pc["seed"])
     res = m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), silence_tokens=gu.SILENCE, **meta["kw"])[0]
     assert np.array_equal(res.cpu().numpy(), g[f"pin{j}_res"].astype(np.int64)), "token ids differ from the reference at 830M"
+
+
+def test_config1_330M_head_dim_64_matches_reference():
+    """BASELINE.json configs[0]: 323M stand-in, d=1024, 24 layers, 16 heads -> head_dim 64,
+    one utterance, 3 s prompt -> 5 s generated (250 frames + the K-step end cascade), top-k 40, seed 1.  The fixture is
+    the UNMODIFIED reference's output (tests/golden/make_golden_cfg1.py); fp32 KV, same CPU-generator noise.
+    head_dim 64 takes the per-kernel decode path (attn_rows_kernel<*, 64>, d=1024 GEMM shapes)."""
+    from voicecraft_b200 import synthetic
+    g = np.load(os.path.join(gu.GOLDEN, "lm_cfg1_330m.npz"))
+    cfg = synthetic.make_config("330M")
+    sd = gu.suppress_end_tokens(cfg, synthetic.make_state_dict(cfg, seed=0))
+    x, xl, y = torch.from_numpy(g["x"]), torch.from_numpy(g["x_lens"]), torch.from_numpy(g["y"])
+    m = _model(cfg, sd, "fp32")
+    m.noise_fn = gu.cpu_noise_fn(1)
+    m.trace_logits = []
+    res = m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), silence_tokens=gu.SILENCE, top_k=40, top_p=1.0, temperature=1.0,
+                          stop_repetition=3)[0]
+    for step, ref in zip(g["trace_steps"], g["trace_logits"]):
+        got = m.trace_logits[int(step)].cpu().numpy()
+        live = ref > -9999
+        assert float(np.abs(got - ref)[live].max()) <= LOGIT_TOL, f"step {step}"
+    assert len(m.trace_logits) == int(g["n_steps"])
+    assert np.array_equal(res.cpu().numpy(), g["res"].astype(np.int64)), "token ids differ from the reference on config 1"
+
+
+def test_continuous_batching_equals_single_calls():
+    """10 utterances of different lengths through 4 slots with refill-on-finish; every result
+    equals `torch.manual_seed(seed_i); inference_tts(utterance i)`."""
+    from voicecraft_b200 import synthetic
+    from voicecraft_b200.voicecraft import ContinuousBatcher
+    cfg = synthetic.make_config("tiny")
+    sd = synthetic.make_state_dict(cfg, seed=46)
+    sd["predict_layer.0.2.bias"][cfg.eos] += 4.5
+    m = _model(cfg, sd, "bf16")
+    utts = [synthetic.synthetic_utterance(cfg, 800 + i, text_len=3 + i % 4, prompt_frames=8 + 6 * (i % 5)) for i in range(10)]
+    seeds = [300 + 7 * i for i in range(10)]
+    kw = dict(top_k=40, top_p=1.0, temperature=1.0, stop_repetition=3)
+    singles = []
+    for (x, xl, y), s in zip(utts, seeds):
+        torch.manual_seed(s)
+        singles.append(m.inference_tts(x.cuda(), xl.cuda(), y.cuda(), **kw)[0])
+    cb = ContinuousBatcher(m, max_concurrency=4, poll_every=3, **kw)
+    for (x, xl, y), s in zip(utts, seeds):
+        cb.submit(x, y, seed=s)
+    out = cb.run()
+    assert cb.stats["prefills"] >= 3 and cb.stats["max_active"] == 4
+    for i, (a, (b, _)) in enumerate(zip(singles, out)):
+        assert torch.equal(a, b), f"utterance {i}"

@@ -79,3 +79,25 @@ def test_kv_bf16_policy_is_close():
     got0 = trace[0].reshape(-1, ref0.shape[-1]).numpy()
     live = ref0 > -9999
     assert np.abs(got0 - ref0)[live].max() < 5e-2
+
+
+def test_oracle_reproduces_config1_prefix():
+    """BASELINE.json configs[0] on the CPU oracle: the first sampled steps of the 323M / head_dim-64 utterance equal the
+    unmodified reference's fixture (the full 254-step equality is asserted when the fixture is generated)."""
+    import os
+    import numpy as np
+    import torch
+    import golden_util as gu
+    from oracle import lm_oracle
+    from voicecraft_b200 import synthetic
+    g = np.load(os.path.join(gu.GOLDEN, "lm_cfg1_330m.npz"))
+    cfg = synthetic.make_config("330M")
+    sd = gu.suppress_end_tokens(cfg, synthetic.make_state_dict(cfg, seed=0))
+    x, xl, y = torch.from_numpy(g["x"]), torch.from_numpy(g["x_lens"]), torch.from_numpy(g["y"])
+    n = 6
+    rows = lm_oracle.OracleLM(cfg, sd).inference_tts(x, xl, y, silence_tokens=gu.SILENCE, noise_fn=gu.cpu_noise_fn(1),
+                                                     max_steps=n, top_k=40, top_p=1.0, temperature=1.0, stop_repetition=3)
+    K, T = cfg.n_codebooks, y.shape[1]
+    res = g["res"].astype(np.int64)[0]              # [K, T + G], un-delayed: frame t of codebook k was sampled at step t + k
+    for k in range(K):
+        assert np.array_equal(rows[k: n, k].numpy(), res[k, T: T + n - k]), k

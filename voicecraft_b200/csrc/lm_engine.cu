@@ -129,6 +129,9 @@ struct vcb_engine {
     int opt_mega = 1, mega_grid = 0, mega_nph = 0, mega_cnt_stride = 0;
     MegaPhase* d_mega_ph[2] = {nullptr, nullptr};
     CUtensorMap* d_wmaps = nullptr;        // device copies of the weight tensor maps: [L][qkv, out, ff1, ff2], h1
+    const void** d_wptrs = nullptr;        // raw packed-weight pointers, same order, then the K second-stage head matrices
+    int mega_ns = 11, mega_nb = 6, mega_pf = 0;
+    unsigned long long* mega_tl = nullptr;   // debug timeline of the persistent kernel (vcb_debug_mega_timeline)
     unsigned int* mega_flags = nullptr;
     int* mega_tile_cnt = nullptr;
     float* mega_part = nullptr;
@@ -682,10 +685,11 @@ int mega_build(vcb_engine* e, int bpad) {
     auto emit = [&](GemmEpilogue& ep, const float* gamma_next, __nv_bfloat16* dst) {
         ep.emit = 1; ep.next_gamma = gamma_next; ep.next_act = dst; ep.next_ld = m.d; ep.next_bpad = bpad; ep.stats_out = e->ln_stats;
     };
-    auto gemm = [&](const CUtensorMap* tm, int Nout, int Kdim, int b_map) {
+    auto gemm = [&](const CUtensorMap* tm, const void* const* wp, int Nout, int Kdim, int b_map) {
         MegaPhase P;
         P.type = MEGA_GEMM;
         P.tmA = tm;
+        P.wptr = wp;
         P.Nout = Nout;
         P.tiles_per_group = (Nout + 127) / 128;
         P.kb = Kdim / 64;
@@ -696,7 +700,8 @@ int mega_build(vcb_engine* e, int bpad) {
     for (int l = 0; l < m.L; ++l) {
         const Layer& Ly = e->layers[l];
         const CUtensorMap* tm = e->d_wmaps + 4 * l;
-        MegaPhase q = gemm(tm + 0, 3 * m.d, m.d, 0);
+        const void* const* wp = e->d_wptrs + 4 * l;
+        MegaPhase q = gemm(tm + 0, wp + 0, 3 * m.d, m.d, 0);
         q.ep.mode = EPI_QKV; q.ep.qbuf = e->qbuf; q.ep.kpool = Ly.kpool; q.ep.vpool = Ly.vpool; q.ep.page_table = e->page_table;
         q.ep.row_slot = e->row_slot; q.ep.row_pos = e->row_pos; q.ep.row_page = e->row_page; q.ep.kv_fp32 = e->kv_fp32;
         q.ep.max_pages = e->max_pages_per_slot; q.ep.page_size = KV_PAGE; q.ep.d = m.d; q.ep.H = m.H; q.ep.hd = m.hd;
@@ -709,25 +714,25 @@ int mega_build(vcb_engine* e, int bpad) {
         a.vpool = Ly.vpool;
         a.done_target = e->mega_grid;
         ph.push_back(a);
-        MegaPhase o = gemm(tm + 1, m.d, m.d, 0);
+        MegaPhase o = gemm(tm + 1, wp + 1, m.d, m.d, 0);
         o.ep.mode = EPI_RESID; o.ep.bias = Ly.b_out; o.ep.x = e->x_rows; o.ep.ld_out = m.d;
         emit(o.ep, Ly.ln2_g, e->act_d2);
         ph.push_back(o);
-        MegaPhase f1 = gemm(tm + 2, m.F, m.d, 1);
+        MegaPhase f1 = gemm(tm + 2, wp + 2, m.F, m.d, 1);
         f1.ep.mode = EPI_ACT; f1.ep.act = e->act_f; f1.ep.ld_out = m.F; f1.ep.act_kind = 1; f1.ep.bpad_out = bpad;
         fold(f1.ep, Ly.c_ff1, Ly.bp_ff1, dtiles);
         ph.push_back(f1);
-        MegaPhase f2 = gemm(tm + 3, m.d, m.F, 2);
+        MegaPhase f2 = gemm(tm + 3, wp + 3, m.d, m.F, 2);
         f2.ep.mode = EPI_RESID; f2.ep.bias = Ly.b_ff2; f2.ep.x = e->x_rows; f2.ep.ld_out = m.d;
         emit(f2.ep, l + 1 < m.L ? e->layers[l + 1].ln1_g : e->lnf_g, e->act_d);
         ph.push_back(f2);
     }
     const int KH = m.K * m.Hh;
-    MegaPhase h1 = gemm(e->d_wmaps + 4 * m.L, KH, m.d, 0);
+    MegaPhase h1 = gemm(e->d_wmaps + 4 * m.L, e->d_wptrs + 4 * m.L, KH, m.d, 0);
     h1.ep.mode = EPI_ACT; h1.ep.act = e->act_h; h1.ep.ld_out = KH; h1.ep.act_kind = 2; h1.ep.bpad_out = bpad;
     fold(h1.ep, e->c_h1, e->bp_h1, dtiles);
     ph.push_back(h1);
-    MegaPhase h2 = gemm(e->d_h2_maps, m.V, m.Hh, 3);
+    MegaPhase h2 = gemm(e->d_h2_maps, e->d_wptrs + 4 * m.L + 1, m.V, m.Hh, 3);
     h2.groups = m.K;
     h2.b_grp_stride = m.Hh;
     h2.col_grp_stride = m.Vpad;
@@ -769,7 +774,8 @@ int mega_setup(vcb_engine* e) {
             dalloc(&e->mega_part, mega_part_floats(grid, 32)) || dalloc(&e->knew, static_cast<size_t>(R) * m.d) ||
             dalloc(&e->vnew, static_cast<size_t>(R) * m.d) ||
             dalloc(&e->mega_att_ws, static_cast<size_t>(32) * m.H * MEGA_ATT_MAXC * (m.hd + 2)) ||
-            dalloc(&e->mega_att_cnt, static_cast<size_t>(32) * m.H) || dalloc(&e->d_wmaps, static_cast<size_t>(4) * m.L + 1))
+            dalloc(&e->mega_att_cnt, static_cast<size_t>(32) * m.H) || dalloc(&e->d_wmaps, static_cast<size_t>(4) * m.L + 1) ||
+            dalloc(&e->d_wptrs, static_cast<size_t>(4) * m.L + 1 + m.K))
             return -1;
         VCB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->mega_dbg_h), 64, cudaHostAllocMapped));
         memset(e->mega_dbg_h, 0, 64);
@@ -784,6 +790,23 @@ int mega_setup(vcb_engine* e) {
     }
     maps[4 * m.L] = e->h1.tm;
     VCB_CUDA_OK(cudaMemcpy(e->d_wmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    std::vector<const void*> wp(4 * m.L + 1 + m.K);
+    for (int l = 0; l < m.L; ++l) {
+        wp[4 * l + 0] = e->layers[l].qkv.w;
+        wp[4 * l + 1] = e->layers[l].out.w;
+        wp[4 * l + 2] = e->layers[l].ff1.w;
+        wp[4 * l + 3] = e->layers[l].ff2.w;
+    }
+    wp[4 * m.L] = e->h1.w;
+    for (int k = 0; k < m.K; ++k) wp[4 * m.L + 1 + k] = e->h2[k].w;
+    VCB_CUDA_OK(cudaMemcpy(e->d_wptrs, wp.data(), wp.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    if (getenv("VCB_MEGA_NS")) e->mega_ns = atoi(getenv("VCB_MEGA_NS"));
+    if (getenv("VCB_MEGA_NB")) e->mega_nb = atoi(getenv("VCB_MEGA_NB"));
+    if (getenv("VCB_MEGA_PF")) e->mega_pf = atoi(getenv("VCB_MEGA_PF"));
+    if (e->mega_ns < 2 || e->mega_ns > 13 || e->mega_nb < 2 || e->mega_nb > 8 || e->mega_ns * 16384 + e->mega_nb * 8192 > 14 * 16384) {
+        set_error("VCB_MEGA_NS / VCB_MEGA_NB: need 2 <= ns <= 13, 2 <= nb <= 8, ns * 16 KB + nb * 8 KB <= 224 KB");
+        return -1;
+    }
     e->mega_grid = grid;
     if (mega_build(e, 16) || mega_build(e, 32)) return -1;
     return 0;
@@ -802,11 +825,15 @@ int mega_step(vcb_engine* e, int n, cudaStream_t st) {
     a.nvalid = n;
     a.bpad = bpad;
     a.kv_fp32 = e->kv_fp32;
+    a.ns = e->mega_ns;
+    a.nb = e->mega_nb;
+    a.pf = e->mega_pf;
     a.flags = e->mega_flags;
     a.tile_cnt = e->mega_tile_cnt;
     a.tile_cnt_stride = e->mega_cnt_stride;
     a.part = e->mega_part;
     a.dbg = e->mega_dbg_d;
+    a.tl = e->mega_tl;
     a.qbuf = e->qbuf;
     a.knew = e->knew;
     a.vnew = e->vnew;
@@ -1063,8 +1090,8 @@ int vcb_destroy(vcb_engine* e) {
                     e->act_d, e->act_d2, e->act_f, e->act_h, e->row_slot, e->row_pos, e->row_last, e->row_page, e->row_forced, e->row_pages, e->all_rows, e->page_table, e->wx, e->wq, e->w_att_ws, e->w_att_cnt, e->wact_d, e->wact_f,
                     e->d_slots, e->tok_log, e->dbg_logits, e->st, e->gr, e->d_seqs};
     for (void* p : ptrs) cudaFree(p);
-    void* mptrs[] = {e->d_mega_ph[0], e->d_mega_ph[1], e->d_wmaps, e->mega_flags, e->mega_tile_cnt, e->mega_part, e->knew, e->vnew,
-                     e->mega_att_ws, e->mega_att_cnt};
+    void* mptrs[] = {e->d_mega_ph[0], e->d_mega_ph[1], e->d_wmaps, e->d_wptrs, e->mega_flags, e->mega_tile_cnt, e->mega_part, e->knew, e->vnew,
+                     e->mega_att_ws, e->mega_att_cnt, e->mega_tl};
     for (void* p : mptrs) cudaFree(p);
     if (e->mega_dbg_h) cudaFreeHost(e->mega_dbg_h);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1772,6 +1799,25 @@ int vcb_debug_exponential(float* out_dev, int64_t numel, uint64_t seed, uint64_t
     debug_exponential_kernel<<<256, 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, static_cast<unsigned long long>(numel), seed,
                                                                                    offset, static_cast<unsigned int>(threads));
     VCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Debug timeline of the persistent decode-step kernel: the first call enables recording, later calls copy the last
+// step's records out: [2 CTAs (first, last)][n_phases][8 events] %globaltimer ns (0 = event not recorded).
+int vcb_debug_mega_timeline(vcb_engine* e, uint64_t* out_host, int32_t max_records, int32_t* n_phases) {
+    if (!e || e->mega_grid <= 0) {
+        set_error("persistent decode kernel not active");
+        return -1;
+    }
+    const size_t n = static_cast<size_t>(2) * e->mega_nph * 8;
+    if (!e->mega_tl) {
+        VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->mega_tl), n * 8));
+        VCB_CUDA_OK(cudaMemset(e->mega_tl, 0, n * 8));
+    }
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    if (out_host && max_records > 0)
+        VCB_CUDA_OK(cudaMemcpy(out_host, e->mega_tl, std::min<size_t>(n, max_records) * 8, cudaMemcpyDeviceToHost));
+    if (n_phases) *n_phases = e->mega_nph;
     return 0;
 }
 

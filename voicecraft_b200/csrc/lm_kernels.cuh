@@ -513,7 +513,8 @@ __device__ __forceinline__ float torch_exponential_at(unsigned long long seed, u
     const uint32_t x = comp == 0 ? o.x : comp == 1 ? o.y : comp == 2 ? o.z : o.w;
     // curand_uniform: x * 2^-32 + 2^-33 (the product is exact, one rounding in the add), range (0, 1]
     const float u = __fadd_rn(__fmul_rn(static_cast<float>(x), 2.3283064365386963e-10f), 1.16415321826934814453e-10f);
-    const float lg = (u >= 1.0f - 1.1920928955078125e-07f / 2) ? -1.1920928955078125e-07f / 2 : logf(u);
+    // at::log is __logf in device code (ATen/NumericUtils.h), which is why the transform guards u ~ 1
+    const float lg = (u >= 1.0f - 1.1920928955078125e-07f / 2) ? -1.1920928955078125e-07f / 2 : __logf(u);
     return -lg;                                                 // (-1 / lambda) * log with lambda = 1
 }
 // philox offset consumed by one draw of numel elements (ATen calc_execution_policy: counter_offset)

@@ -34,26 +34,27 @@ namespace vcb {
 static constexpr int MG_THREADS = 384;
 static constexpr int MG_WORKERS = 256;
 static constexpr int MG_SLOT = 16384;          // ring slot = one 128 x 64 bf16 weight block = one bf16 K (or V) slab
-static constexpr int MG_NS = 11;               // ring slots
-static constexpr int MG_NB = 6;                // activation (B operand) ring slots
+static constexpr int MG_NS_MAX = 13;           // ring slots (MegaArgs::ns of them are used)
+static constexpr int MG_NB_MAX = 8;            // activation (B operand) ring slots (MegaArgs::nb)
+static constexpr int MG_POOL = 14 * 16384;     // bytes shared by the two rings: ns * 16 KB + nb * 8 KB <= MG_POOL
 static constexpr int MG_BSLOT = 8192;          // 64 rows (32 hi + 32 lo) x 64 k, bf16
 static constexpr int MG_NACC = 4;              // TMEM accumulator stages
 static constexpr int MG_HD = 128;
 static constexpr int MG_PAGE = 64;
 
 struct MegaSmem {
-    static constexpr int RING = 0;
-    static constexpr int BRING = MG_NS * MG_SLOT;                  // attention scratch aliases this region
-    static constexpr int BAR = BRING + MG_NB * MG_BSLOT;
-    static constexpr int NBAR = 2 * MG_NS + 2 * MG_NB + 2 * MG_NACC;
-    static constexpr int MISC = BAR + NBAR * 8;                    // tmem slot, flags, page-count table
-    static constexpr int TOTAL = MISC + 16 + 34 * 4 + 64;
+    static constexpr int RING = 0;                                  // ns slots, then the B ring (attention scratch aliases it)
+    static constexpr int BAR = MG_POOL;
+    static constexpr int NBAR = 2 * MG_NS_MAX + 2 * MG_NB_MAX + 2 * MG_NACC;
+    static constexpr int MISC = BAR + NBAR * 8;                    // tmem slot, flags, producer progress, page-count table
+    static constexpr int TOTAL = MISC + 32 + 34 * 4 + 64;
     // attention scratch inside BRING
     static constexpr int A_SC = 0;                                  // scores, double buffered: 2 x 64 floats
     static constexpr int A_PW = 512;                                // per-warp probabilities: 8 x 64 floats
     static constexpr int A_RED = A_PW + 8 * MG_PAGE * 4;            // per-warp partial outputs: 8 x 128 floats
 };
-static_assert(MegaSmem::A_RED + 8 * MG_HD * 4 <= MG_NB * MG_BSLOT, "attention scratch must fit the B ring");
+static_assert(MegaSmem::A_RED + 8 * MG_HD * 4 <= 2 * MG_BSLOT, "attention scratch must fit two B slots");
+static_assert(MegaSmem::TOTAL <= 232448, "shared memory budget of one CTA per SM");
 
 __device__ __forceinline__ unsigned int mg_ld_acquire(const unsigned int* p) {
     unsigned int v;
@@ -105,10 +106,21 @@ __device__ __forceinline__ void mg_wait_flag(const unsigned int* flag, unsigned 
 }
 __device__ __forceinline__ void mg_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// range of CTA c over T work units, and the CTA that owns unit u
-__device__ __forceinline__ void mg_range(long long T, int c, int G, int& b0, int& b1) {
-    b0 = static_cast<int>(T * c / G);
-    b1 = static_cast<int>(T * (c + 1) / G);
+// Work split of T units over the first Ge = min(G, T) CTAs (every one of them gets >= 1 unit, the others none, so the
+// CTAs that share a tile / an attention item are always consecutive): range of CTA c, and the CTA that owns unit u.
+__device__ __forceinline__ int mg_eff(long long T, int G) { return static_cast<int>(T < G ? T : G); }
+__device__ __forceinline__ void mg_range(long long T, int c, int Ge, int& b0, int& b1) {
+    if (c >= Ge) {
+        b0 = b1 = 0;
+        return;
+    }
+    b0 = static_cast<int>(T * c / Ge);
+    b1 = static_cast<int>(T * (c + 1) / Ge);
+}
+// debug timeline: CTA 0 and the last CTA record %globaltimer at fixed (phase, event) slots
+__device__ __forceinline__ void mg_tl(const MegaArgs& A, int p, int ev) {
+    if (A.tl != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+        A.tl[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * A.nph + p) * 8 + ev] = mg_now();
 }
 __device__ __forceinline__ int mg_owner(long long u, long long T, int G) { return static_cast<int>(((u + 1) * G - 1) / T); }
 
@@ -340,28 +352,30 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
     constexpr int NSL = MG_PAGE / TPS;                    // ring slots per K (or V) slab
     using L = MegaSmem;
     extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t MG_NS = A.ns, MG_NB = A.nb;             // ring depths (runtime: swept by VCB_MEGA_NS / VCB_MEGA_NB)
     uint8_t* ring = smem + L::RING;
-    uint8_t* bring = smem + L::BRING;
+    uint8_t* bring = smem + L::RING + MG_NS * MG_SLOT;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR);
-    uint64_t* empty = full + MG_NS;
-    uint64_t* bfull = empty + MG_NS;
-    uint64_t* bempty = bfull + MG_NB;
-    uint64_t* accfull = bempty + MG_NB;
+    uint64_t* empty = full + MG_NS_MAX;
+    uint64_t* bfull = empty + MG_NS_MAX;
+    uint64_t* bempty = bfull + MG_NB_MAX;
+    uint64_t* accfull = bempty + MG_NB_MAX;
     uint64_t* accempty = accfull + MG_NACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::MISC);
     int* s_flag = reinterpret_cast<int*>(smem + L::MISC + 8);
-    int* s_cum = reinterpret_cast<int*>(smem + L::MISC + 16);           // [33] prefix sum of pages per row
+    volatile uint32_t* s_prod = reinterpret_cast<volatile uint32_t*>(smem + L::MISC + 16);   // ring items issued so far
+    int* s_cum = reinterpret_cast<int*>(smem + L::MISC + 32);           // [33] prefix sum of pages per row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, G = gridDim.x;
     const MegaPhase* __restrict__ ph = A.ph;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < MG_NS; ++i) {
+        for (uint32_t i = 0; i < MG_NS; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 8);          // weights: 7 lanes of the MMA warp + its commit; K/V slabs: the 8 worker warps
         }
-        for (int i = 0; i < MG_NB; ++i) {
+        for (uint32_t i = 0; i < MG_NB; ++i) {
             mbar_init(&bfull[i], 1);
             mbar_init(&bempty[i], 1);
         }
@@ -370,6 +384,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
             mbar_init(&accempty[i], 8);
         }
         mbar_fence_init();
+        *s_prod = 0u;
         int c = 0;
         for (int r = 0; r < 32; ++r) {
             s_cum[r] = c;
@@ -388,7 +403,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     const long long U = static_cast<long long>(A.H) * s_cum[32];     // attention units of this step
     int u0, u1;
-    mg_range(U, cta, G, u0, u1);
+    const int Ue = mg_eff(U, G);
+    mg_range(U, cta, Ue, u0, u1);
     const int att_items = (u1 - u0) * 2 * NSL;                        // ring items of one attention phase (this CTA)
 
     if (warp == 0) {
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 const int s = it % MG_NS;
                 if (it >= MG_NS) mg_wait(&empty[s], ((it / MG_NS) - 1) & 1, A.dbg, 0, p);
                 ++it;
+                *s_prod = it;
                 return s;
             };
             for (int p = 0; p < A.nph; ++p) {
@@ -407,7 +424,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 if (P.type == MEGA_GEMM) {
                     const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
                     int b0, b1;
-                    mg_range(T, cta, G, b0, b1);
+                    const int Ge = mg_eff(T, G);
+                    mg_range(T, cta, Ge, b0, b1);
                     for (int blk = b0; blk < b1; ++blk) {
                         const int tile = blk / P.kb, kbi = blk - tile * P.kb;
                         const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
@@ -449,6 +467,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                         }
                     }
                 }
+                mg_tl(A, p, 7);
             }
         }
     } else if (warp == 1) {
@@ -463,7 +482,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
             }
             const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
             int b0, b1;
-            mg_range(T, cta, G, b0, b1);
+            const int Ge = mg_eff(T, G);
+                    mg_range(T, cta, Ge, b0, b1);
             int blk = b0;
             while (blk < b1) {
                 const int tile = blk / P.kb;
@@ -501,9 +521,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 if (P.type != MEGA_GEMM) continue;
                 const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
                 int b0, b1;
-                mg_range(T, cta, G, b0, b1);
+                const int Ge = mg_eff(T, G);
+                    mg_range(T, cta, Ge, b0, b1);
                 if (b0 >= b1) continue;
                 if (P.dep_target > 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 3, p);
+                mg_tl(A, p, 0);
                 mg_fence_proxy_async();              // other CTAs' generic-proxy stores -> visible to my TMA loads
                 for (int blk = b0; blk < b1; ++blk, ++bit) {
                     const int tile = blk / P.kb, kbi = blk - tile * P.kb;
@@ -512,6 +534,71 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     if (bit >= MG_NB) mg_wait(&bempty[bs], ((bit / MG_NB) - 1) & 1, A.dbg, 3, p);
                     mbar_arrive_expect_tx(&bfull[bs], B_BYTES);
                     tma_load_2d(bring + bs * MG_BSLOT, &A.tmB[P.b_map], &bfull[bs], P.b_col_off + g * P.b_grp_stride + kbi * 64, 0);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== L2 prefetcher: walks the same schedule `pf` items ahead of the ring producer ===============================
+        // The ring holds ns * 16 KB per SM; while a dependency chain resolves and the ring is full, HBM would idle.  This
+        // thread keeps pulling the items AFTER the ring's window from HBM into L2 (cp.async.bulk.prefetch.L2), so that when
+        // slots free up the ring refills at L2 speed.
+        if (lane == 0 && A.pf > 0) {
+            uint32_t it = 0;
+            auto pace = [&](int p) {
+                // stay at most pf items ahead of the producer
+                unsigned long long t0 = 0;
+                for (unsigned int spins = 0; it >= *s_prod + MG_NS + static_cast<uint32_t>(A.pf); ++spins) {
+                    __nanosleep(64);
+                    if ((spins & 0xfffu) == 0xfffu) {
+                        const unsigned long long t = mg_now();
+                        if (t0 == 0) t0 = t;
+                        else if (t - t0 > 4000000000ull) return false;      // producer stuck: its own watchdog reports
+                    }
+                }
+                return true;
+            };
+            bool ok = true;
+            for (int p = 0; p < A.nph && ok; ++p) {
+                const MegaPhase& P = ph[p];
+                if (P.type == MEGA_GEMM) {
+                    const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
+                    int b0, b1;
+                    const int Ge = mg_eff(T, G);
+                    mg_range(T, cta, Ge, b0, b1);
+                    for (int blk = b0; blk < b1 && ok; ++blk, ++it) {
+                        if (it < MG_NS) continue;                            // the first window goes straight to the ring
+                        ok = pace(p);
+                        const int tile = blk / P.kb, kbi = blk - tile * P.kb;
+                        const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
+                        tma_prefetch_l2(static_cast<const uint8_t*>(P.wptr[g]) + static_cast<size_t>(tl * P.kb + kbi) * MG_SLOT, MG_SLOT);
+                    }
+                } else {
+                    int r = 0;
+                    while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u0) ++r;
+                    int npg = s_cum[r + 1] - s_cum[r];
+                    int rem = u0 - A.H * s_cum[r];
+                    int h = npg ? rem / npg : 0, pg = npg ? rem - h * npg : 0;
+                    const KVT* kpool = static_cast<const KVT*>(P.kpool);
+                    const KVT* vpool = static_cast<const KVT*>(P.vpool);
+                    for (int u = u0; u < u1 && ok; ++u, it += 2 * NSL) {
+                        if (it >= MG_NS) {
+                            ok = pace(p);
+                            const int page = A.row_pages[r * A.max_pages + pg];
+                            const size_t off = (static_cast<size_t>(page) * A.H + h) * MG_PAGE * MG_HD;
+                            tma_prefetch_l2(kpool + off, NSL * MG_SLOT);
+                            tma_prefetch_l2(vpool + off, NSL * MG_SLOT);
+                        }
+                        if (++pg == npg) {
+                            pg = 0;
+                            if (++h == A.H) {
+                                h = 0;
+                                do {
+                                    ++r;
+                                    npg = r < 32 ? s_cum[r + 1] - s_cum[r] : 1;
+                                } while (r < 32 && npg == 0);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -527,7 +614,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
             if (P.type == MEGA_GEMM) {
                 const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
                 int b0, b1;
-                mg_range(T, cta, G, b0, b1);
+                const int Ge = mg_eff(T, G);
+                    mg_range(T, cta, Ge, b0, b1);
                 const int first_tile = b0 / P.kb;
                 int blk = b0;
                 while (blk < b1) {
@@ -539,6 +627,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     mg_wait(&accfull[stage], (seg / MG_NACC) & 1, A.dbg, 4, p);
                     tc_fence_after();
                     ++seg;
+                    if (wtid == 0) mg_tl(A, p, 1);
                     // ---- TMEM -> registers: feature = TMEM lane, my group's half of the rows (hi + lo columns) ----------
                     const uint32_t taddr = tmem_base + stage * BN + (static_cast<uint32_t>(q * 32) << 16);
                     float v[HB];
@@ -567,14 +656,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     for (int j = 0; j < HB; ++j) __stcg(pdst + (grp * HB + j) * 128, v[j]);
                     __threadfence();
                     mg_bar_workers();
-                    const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, G);
-                    const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, G);
+                    const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, Ge);
+                    const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, Ge);
                     const int ncontrib = c_last - c_first + 1;
                     if (wtid == 0) *s_flag = (atomicAdd(A.tile_cnt + p * A.tile_cnt_stride + tile, 1) == ncontrib - 1);
                     mg_bar_workers();
                     if (*s_flag) {
                         __threadfence();
-                        mg_tile_epilogue<BPAD>(A, P, p, tile, c_first, ncontrib, T, G, wq, lane);
+                        mg_tile_epilogue<BPAD>(A, P, p, tile, c_first, ncontrib, T, Ge, wq, lane);
                         __threadfence();
                         mg_bar_workers();
                         if (wtid == 0) {
@@ -582,10 +671,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             mg_fence_proxy_async();
                             __threadfence();
                             atomicAdd(A.flags + p, 1u);
+                            mg_tl(A, p, 2);
                         }
                     } else {
                         mg_bar_workers();                 // s_flag is rewritten by the next tile
                     }
+                    if (wtid == 0) mg_tl(A, p, 3);
                 }
             } else {
                 // ===== attention: units [u0, u1) ========================================================================
@@ -597,6 +688,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     if (lane == 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 5, p);
                     __syncwarp();
                 }
+                if (wtid == 0) mg_tl(A, p, 4);
                 const int sub = lane % LPT;
                 int r = 0;
                 while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u0) ++r;
@@ -722,7 +814,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     } else {
                         // item shared with neighbouring CTAs: publish (o, m, l); the last arriver merges in CTA order
                         const long long ui0 = static_cast<long long>(A.H) * s_cum[r] + static_cast<long long>(h) * npg;
-                        const int c_first = mg_owner(ui0, U, G), c_last = mg_owner(ui0 + npg - 1, U, G);
+                        const int c_first = mg_owner(ui0, U, Ue), c_last = mg_owner(ui0 + npg - 1, U, Ue);
                         const int nch = c_last - c_first + 1;
                         float* base = A.att_ws + static_cast<size_t>(rh) * MEGA_ATT_MAXC * (MG_HD + 2);
                         float* myws = base + static_cast<size_t>(cta - c_first) * (MG_HD + 2);
@@ -776,12 +868,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     }
                 }
                 // this CTA's share of the phase is done (merged outputs are counted by whoever merged them)
+                if (wtid == 0) mg_tl(A, p, 5);
                 __threadfence();
                 mg_bar_workers();
                 if (wtid == 0) {
                     mg_fence_proxy_async();
                     __threadfence();
                     atomicAdd(A.flags + p, 1u);
+                    mg_tl(A, p, 6);
                 }
             }
         }

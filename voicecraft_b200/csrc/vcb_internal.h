@@ -78,6 +78,7 @@ struct MegaPhase {
     int groups = 1, tiles_per_group = 0, kb = 0, Nout = 0;
     int b_map = 0, b_col_off = 0, b_grp_stride = 0, col_grp_stride = 0;
     const CUtensorMap* tmA = nullptr;         // device array [groups]
+    const void* const* wptr = nullptr;        // device array [groups]: packed weights (contiguous 16 KB blocks), L2 prefetch
     const float* const* grp_bias = nullptr;   // device array [groups] or null (ep.bias)
     GemmEpilogue ep;
     // ATTN: this layer's pools
@@ -90,11 +91,14 @@ struct MegaArgs {
     CUtensorMap tmB[4];                 // activation operands: 0 act_d, 1 act_d2, 2 act_f, 3 act_h
     const MegaPhase* ph = nullptr;      // device array
     int nph = 0, nvalid = 0, bpad = 0, kv_fp32 = 0;
+    int ns = 11, nb = 6;                // ring depths: ns * 16 KB + nb * 8 KB <= 224 KB
+    int pf = 0;                         // L2 prefetch distance in ring items (0 = off)
     unsigned int* flags = nullptr;      // [nph] completion counters (zeroed by step_prep)
     int* tile_cnt = nullptr;            // [nph][max tiles] split-K arrival counters (self-resetting)
     int tile_cnt_stride = 0;
     float* part = nullptr;              // [grid][MEGA_MAXSEG][bpad][128] split-K partials
     unsigned int* dbg = nullptr;        // watchdog record
+    unsigned long long* tl = nullptr;   // debug timeline [2 CTAs][nph][8 events] of %globaltimer (null: off)
     // attention
     const float* qbuf = nullptr;
     const float* knew = nullptr;

@@ -158,3 +158,20 @@ class AudioTokenizer:
     def decode(self, frames) -> torch.Tensor:
         """Reference signature: frames = [(codes[1,K,T], None)] (data/tokenizer.py:131-133)."""
         return self.decode_codes(frames[0][0])
+
+
+def save_wav(path, wav: torch.Tensor, sample_rate: int):
+    """Write a decoded waveform ([1, C, N] / [C, N] / [N] float in [-1, 1]) as 16-bit PCM -- the serialisation step of the
+    reference's drivers (torchaudio.save at inference_tts_scale.py:191) without the torchaudio dependency."""
+    import wave
+    w = wav.detach().float().cpu()
+    while w.dim() > 2:
+        w = w[0]
+    if w.dim() == 1:
+        w = w.unsqueeze(0)
+    pcm = (w.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16).t().contiguous().numpy()     # [N, C] interleaved
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(int(w.shape[0]))
+        f.setsampwidth(2)
+        f.setframerate(int(sample_rate))
+        f.writeframes(pcm.tobytes())

@@ -775,3 +775,114 @@ class DecodeSession:
                 self.lib.vcb_release(self.eng, s, 1)
             self._open = False
         self.model._sessions.discard(self)
+
+
+class ContinuousBatcher:
+    """Continuous batching of independent TTS utterances.
+
+    The reference synthesises one utterance per call in a Python loop (inference_tts_scale.py:43-105; the sentence loop of
+    gradio_app.py:248-313).  Here up to `max_concurrency` utterances decode together; the moment one finishes, its tokens
+    are read, its slot and KV pages are released and the next queued utterance is prefilled into the free slot while the
+    others keep decoding.  Every utterance owns its random stream (`seed`), so its result is exactly what
+    ``torch.manual_seed(seed); model.inference_tts(x, x_lens, y, ...)`` returns, whatever it was batched with.
+    """
+
+    def __init__(self, model: "VoiceCraft", max_concurrency=32, poll_every=8, top_k=-100, top_p=1.0, temperature=1.0,
+                 stop_repetition=3, silence_tokens=(1388, 1898, 131)):
+        self.model, self.B, self.poll_every = model, int(max_concurrency), max(1, int(poll_every))
+        self.sp = model._sampling(top_k, top_p, temperature, stop_repetition, silence_tokens)
+        self.queue, self.slots, self._open = [], [], False
+        self.stats = dict(steps=0, prefills=0, max_active=0)
+
+    def submit(self, x, y, seed=None):
+        """x [1,L] int64, y [1,T,K] int64 (host or device).  Returns the ticket (index into run()'s result list)."""
+        self.queue.append((x, y, seed))
+        return len(self.queue) - 1
+
+    @torch.no_grad()
+    def run(self):
+        m, a = self.model, self.model.args
+        if m.noise_fn is not None:
+            raise _lib.VcbError("ContinuousBatcher uses the per-utterance device generators (model.noise_fn must be None)")
+        K, dev, lib = a.n_codebooks, m.mask_embedding.device, _lib.load()
+        V = m.n_audio_tokens[0]
+        jobs, need_seq = [], 0
+        for x, y, seed in self.queue:
+            x = x.to(dev, non_blocking=True)
+            y = y.to(dev, non_blocking=True)
+            if a.special_first:
+                y = y + int(a.n_special)
+            yk = y.transpose(2, 1)[0].long().contiguous()
+            shifted, _ = m.shift([[yk]])
+            prompt = shifted[0][0][:, : -(K - 1)] if K > 1 else shifted[0][0]
+            y_tok = prompt.transpose(1, 0).contiguous()
+            x_ids = x[0].long().contiguous()
+            m._check_ids(x_ids, y_tok)
+            cap = int(x.shape[1]) * (int(a.encodec_sr) // 5)
+            need_seq = max(need_seq, int(x.shape[1]) + max(int(y_tok.shape[0]), cap + 1) + K + 8)
+            jobs.append(dict(x_ids=x_ids, y_tok=y_tok, yk=yk, seed=seed))
+        n_slots = min(self.B, max(1, len(jobs)))
+        eng = m._engine(need_slots=n_slots, need_seq=need_seq)
+        base = m._free_slots(n_slots, m._eng_opts["max_slots"])
+        self.slots, self._open = [base + i for i in range(n_slots)], True
+        m._sessions.add(self)
+        gen0 = torch.cuda.default_generators[dev.index or 0]
+        seed0, threads = int(gen0.initial_seed()), m._rng_threads(dev, K * V)
+        free, active, results, nxt = list(self.slots), {}, [None] * len(jobs), 0
+        try:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream().cuda_stream
+                steps = 0
+                while nxt < len(jobs) or active:
+                    # ---- refill free slots from the queue: one packed prefill + the first sampling step of the newcomers
+                    new = []
+                    while free and nxt < len(jobs):
+                        new.append((free.pop(0), nxt))
+                        nxt += 1
+                    if new:
+                        P = (_lib.vcb_prompt * len(new))()
+                        for j, (slot, ji) in enumerate(new):
+                            J = jobs[ji]
+                            P[j] = _lib.vcb_prompt(slot=slot, n_copies=1, mode=0, x_len=int(J["x_ids"].shape[0]),
+                                                   text_ids_dev=J["x_ids"].data_ptr(), y_len=int(J["y_tok"].shape[0]),
+                                                   y_tokens_dev=J["y_tok"].data_ptr(), mask_rows_dev=None, n_more_spans=0)
+                            P[j].rng_seed = (int(J["seed"]) if J["seed"] is not None else seed0 + ji) & 0xFFFFFFFFFFFFFFFF
+                            P[j].rng_offset = 0
+                            P[j].rng_threads = threads
+                        _lib.check(lib.vcb_prefill(eng, P, len(new), stream))
+                        for slot, ji in new:
+                            active[slot] = ji
+                        c_new = (C.c_int32 * len(new))(*[s for s, _ in new])
+                        _lib.check(lib.vcb_sample(eng, c_new, len(new), None, C.byref(self.sp), stream))
+                        self.stats["prefills"] += 1
+                    order = sorted(active)
+                    c_slots = (C.c_int32 * len(order))(*order)
+                    self.stats["max_active"] = max(self.stats["max_active"], len(order))
+                    # ---- decode steps for everyone until the next poll
+                    for _ in range(self.poll_every):
+                        _lib.check(lib.vcb_decode_step(eng, c_slots, len(order), None, C.byref(self.sp), stream))
+                        steps += 1
+                    status = (_lib.vcb_status * len(order))()
+                    _lib.check(lib.vcb_poll(eng, c_slots, len(order), status, stream))
+                    for slot, st in zip(order, status):
+                        if st.done == 2:
+                            raise _lib.VcbError("decode stopped: engine capacity (max_new_tokens / max_seq_len) exhausted; "
+                                                "raise it with configure_engine()")
+                        if st.done:
+                            ji = active.pop(slot)
+                            rows = m._read_rows(eng, slot, st.n_steps, stream)
+                            gen = torch.from_numpy(VoiceCraft._undelay(rows, K)).to(dev)
+                            res = torch.cat([jobs[ji]["yk"], gen], dim=1).unsqueeze(0)
+                            if a.special_first:
+                                res, gen = res - int(a.n_special), gen - int(a.n_special)
+                            results[ji] = (res, gen.unsqueeze(0))
+                            lib.vcb_release(eng, slot, 1)
+                            free.append(slot)
+                self.stats["steps"] = steps
+        finally:
+            for slot in list(active):
+                lib.vcb_release(eng, slot, 1)
+            self._open = False
+            m._sessions.discard(self)
+            self.queue = []
+        return results
