@@ -1,5 +1,7 @@
-"""Per-phase device timeline of the persistent decode-step kernel at the bench shape (830M, B=32): for the first layers,
-when each phase's dependency resolved, when its first accumulator was ready, when this CTA finished, for CTA 0 and the last CTA.
+"""Per-phase device timeline of the persistent decode-step kernel at the bench shape (830M, B=32), over ALL CTAs.
+Events per (cta, phase): 0 dep (B producer saw the previous phase complete), 1 acc (first accumulator of the phase ready),
+2 epi (this CTA finished a tile epilogue as last arriver), 3 end (this CTA's last segment handed over), 4 attention dep,
+5 attention loop end, 6 attention flag published, 7 ring producer issued the phase's last item.
 usage: python scripts/mega_timeline.py [steps_before] [kv]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,26 +21,29 @@ sess.sample()
 for _ in range(steps_before): sess.step()
 nph = C.c_int32()
 _lib.check(lib.vcb_debug_mega_timeline(sess.eng, None, 0, C.byref(nph)))
+G = int(lib.vcb_counter(sess.eng, b"mega_grid"))
 for _ in range(3): sess.step()
-n = 2 * nph.value * 8
+n = G * nph.value * 8
 buf = (C.c_uint64 * n)()
 _lib.check(lib.vcb_debug_mega_timeline(sess.eng, buf, n, C.byref(nph)))
-t = np.frombuffer(buf, dtype=np.uint64).reshape(2, nph.value, 8).astype(np.int64)
-t0 = t[t > 0].min()
+t = np.frombuffer(buf, dtype=np.uint64).reshape(G, nph.value, 8).astype(np.float64)
+t[t == 0] = np.nan
+t0 = np.nanmin(t[:, 0, :])
+t = (t - t0) / 1e3
 names = ["qkv", "attn", "out", "ffn1", "ffn2"]
-print("ctx", 231 + steps_before + 3, "phases", nph.value, "(us since the first record; ev: dep=B producer saw the previous phase done, acc=first accumulator ready,")
-print("  epi=this CTA ran a tile epilogue (last), end=this CTA's work of the phase done, prod=ring producer issued the phase's last item)")
-for c in range(2):
-    print("CTA", "first" if c == 0 else "last")
-    prev_end = None
-    for p in range(min(nph.value, 22)):
-        r = t[c, p]
-        us = lambda v: "%8.2f" % ((v - t0) / 1e3) if v > 0 else "    -   "
-        nm = names[p % 5] if p < nph.value - 2 else ("h1" if p == nph.value - 2 else "h2")
-        if nm == "attn":
-            print(f"  {p:3d} {nm:5s} dep {us(r[4])} loop_end {us(r[5])} flag {us(r[6])} prod {us(r[7])}")
-        else:
-            print(f"  {p:3d} {nm:5s} dep {us(r[0])} acc {us(r[1])} epi {us(r[2])} end {us(r[3])} prod {us(r[7])}")
-    last = t[c][t[c] > 0].max()
-    print("  step kernel span (first..last record): %.1f us" % ((last - t0) / 1e3))
+print("ctx", 231 + steps_before + 3, "grid", G, "phases", nph.value, " -- microseconds since the step's first record; min / median / max over CTAs")
+f = lambda a: "   -  /   -  /   -  " if np.all(np.isnan(a)) else "%6.1f/%6.1f/%6.1f" % (np.nanmin(a), np.nanmedian(a), np.nanmax(a))
+for p in range(nph.value):
+    nm = names[p % 5] if p < nph.value - 2 else ("h1" if p == nph.value - 2 else "h2")
+    if p >= 12 and p < nph.value - 7: continue
+    if nm == "attn":
+        print(f"{p:3d} {nm:5s} dep {f(t[:, p, 4])}  loop_end {f(t[:, p, 5])}  flag {f(t[:, p, 6])}  prod {f(t[:, p, 7])}")
+    else:
+        print(f"{p:3d} {nm:5s} dep {f(t[:, p, 0])}  acc {f(t[:, p, 1])}  end {f(t[:, p, 3])}  epi {f(t[:, p, 2])}  prod {f(t[:, p, 7])}")
+print("kernel span: %.1f us" % np.nanmax(t))
+# per-layer summary over the middle layers
+per = []
+for l in range(2, nph.value // 5 - 1):
+    per.append(np.nanmin(t[:, 5 * (l + 1), 0]) - np.nanmin(t[:, 5 * l, 0]))
+print("per-layer (qkv dep -> next qkv dep): mean %.1f us over %d layers" % (np.mean(per), len(per)))
 sess.close()

@@ -349,7 +349,7 @@ def test_experimental_grouped_prefill_attention(name, monkeypatch):
 # stream per utterance.  Fixtures: tests/golden/lm_830m_b32.* (make_golden_830m.py: the oracle, pinned to the unmodified
 # reference on two full-length 830M utterances).  64 decode steps; contexts 191..541 cross KV-page boundaries, 256 and 512.
 # ==========================================================================================================================
-MARGIN_TOL = {"fp32": 1e-4, "bf16": 1e-2}
+SENS_TOL = {"fp32": 1e-4, "bf16": LOGIT_TOL}    # a token may differ only where a logit move of this size can change it
 
 
 def _headline_run(kv):
@@ -382,13 +382,15 @@ def test_headline_830M_b32_matches_oracle(kv):
     """Token ids of all 32 utterances over 64 sampled steps against the oracle under the same KV policy.
     fp32 KV (the reference's arithmetic): identical, full stop.  bf16 KV pages (the benchmarked policy; oracle
     kv_round_bf16=True): every K/V element is rounded to bf16 from an fp32 value that differs from the CPU's in its last
-    bits, so a sample whose two best p/q scores are closer than the logit noise may legitimately go the other way; the
-    test therefore requires (a) raw logits within LOGIT_TOL of the oracle on the traced steps of still-identical
-    utterances, (b) every utterance identical up to its first differing sample, and that sample to be a certified
-    near-tie of the oracle (relative score margin < MARGIN_TOL), (c) at least 28 of 32 utterances identical throughout."""
+    bits (a 2^-9 relative jump when the rounding goes the other way), so logits carry ~1e-3 of noise and a sample can
+    legitimately change where that is enough to (i) swap the two best p/q scores, (ii) push the winner out of the top-k,
+    or (iii) let an excluded token into the top-k that then wins.  The fixture stores, per sample, the smallest such logit
+    move (`sens`, make_golden_830m.py).  Required: (a) raw logits within LOGIT_TOL of the oracle on the traced steps of
+    still-identical utterances, (b) every utterance identical up to its first differing sample, and that sample's
+    sensitivity below SENS_TOL, (c) at least 28 of 32 utterances identical throughout."""
     meta, g, rows, logits = _headline_run(kv)
     ref = g[f"rows_{kv}"].astype(np.int64)
-    margin = g[f"margin_{kv}"]
+    margin = g[f"sens_{kv}"]
     identical, first_div = 0, {}
     for i in range(32):
         neq = np.argwhere(rows[i] != ref[i])
@@ -408,7 +410,7 @@ def test_headline_830M_b32_matches_oracle(kv):
     print(f"kv={kv}: {identical}/32 identical, divergences {first_div}, max |logit - oracle| {worst:.3g}")
     assert worst <= LOGIT_TOL, f"max |logit - oracle| = {worst}"
     for i, (s, k, mg) in first_div.items():
-        assert mg < MARGIN_TOL[kv], f"utterance {i} differs at step {s} codebook {k} where the oracle's margin is {mg:.3g}"
+        assert mg < SENS_TOL[kv], f"utterance {i} differs at step {s} codebook {k} where the oracle's decision is robust to {mg:.3g}"
     assert identical >= (32 if kv == "fp32" else 28), f"{identical}/32 utterances token-identical ({first_div})"
 
 

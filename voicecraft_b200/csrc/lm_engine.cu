@@ -753,7 +753,6 @@ int mega_setup(vcb_engine* e) {
     e->mega_grid = 0;
     if (!e->opt_mega || !e->opt_fold || e->opt_simt || m.hd != 128 || m.d % 128 || m.F % 128 || (m.K * m.Hh) % 128 || m.Hh % 64) return 0;
     int grid = std::min(mega_max_grid(32, e->kv_fp32), mega_max_grid(16, e->kv_fp32));
-    grid = std::min(grid, (MEGA_ATT_MAXC - 2) * m.H);          // at most MEGA_ATT_MAXC CTAs share one (row, head) item
     if (getenv("VCB_MEGA_GRID")) grid = std::min(grid, atoi(getenv("VCB_MEGA_GRID")));
     if (grid < 1) return 0;
     // a CTA's block range may touch at most MEGA_MAXSEG output tiles of a phase
@@ -773,7 +772,7 @@ int mega_setup(vcb_engine* e) {
         if (dalloc(&e->mega_flags, nph) || dalloc(&e->mega_tile_cnt, static_cast<size_t>(nph) * max_tiles) ||
             dalloc(&e->mega_part, mega_part_floats(grid, 32)) || dalloc(&e->knew, static_cast<size_t>(R) * m.d) ||
             dalloc(&e->vnew, static_cast<size_t>(R) * m.d) ||
-            dalloc(&e->mega_att_ws, static_cast<size_t>(32) * m.H * MEGA_ATT_MAXC * (m.hd + 2)) ||
+            dalloc(&e->mega_att_ws, static_cast<size_t>(32) * m.H * e->max_pages_per_slot * 132) ||
             dalloc(&e->mega_att_cnt, static_cast<size_t>(32) * m.H) || dalloc(&e->d_wmaps, static_cast<size_t>(4) * m.L + 1) ||
             dalloc(&e->d_wptrs, static_cast<size_t>(4) * m.L + 1 + m.K))
             return -1;
@@ -803,8 +802,8 @@ int mega_setup(vcb_engine* e) {
     if (getenv("VCB_MEGA_NS")) e->mega_ns = atoi(getenv("VCB_MEGA_NS"));
     if (getenv("VCB_MEGA_NB")) e->mega_nb = atoi(getenv("VCB_MEGA_NB"));
     if (getenv("VCB_MEGA_PF")) e->mega_pf = atoi(getenv("VCB_MEGA_PF"));
-    if (e->mega_ns < 2 || e->mega_ns > 13 || e->mega_nb < 2 || e->mega_nb > 8 || e->mega_ns * 16384 + e->mega_nb * 8192 > 14 * 16384) {
-        set_error("VCB_MEGA_NS / VCB_MEGA_NB: need 2 <= ns <= 13, 2 <= nb <= 8, ns * 16 KB + nb * 8 KB <= 224 KB");
+    if (e->mega_ns < 2 || e->mega_ns > 13 || e->mega_nb < 3 || e->mega_nb > 8 || e->mega_ns * 16384 + e->mega_nb * 8192 > 14 * 16384) {
+        set_error("VCB_MEGA_NS / VCB_MEGA_NB: need 2 <= ns <= 13, 3 <= nb <= 8, ns * 16 KB + nb * 8 KB <= 224 KB");
         return -1;
     }
     e->mega_grid = grid;
@@ -1803,13 +1802,13 @@ int vcb_debug_exponential(float* out_dev, int64_t numel, uint64_t seed, uint64_t
 }
 
 // Debug timeline of the persistent decode-step kernel: the first call enables recording, later calls copy the last
-// step's records out: [2 CTAs (first, last)][n_phases][8 events] %globaltimer ns (0 = event not recorded).
+// step's records out: [grid CTAs][n_phases][8 events] %globaltimer ns (0 = event not recorded).
 int vcb_debug_mega_timeline(vcb_engine* e, uint64_t* out_host, int32_t max_records, int32_t* n_phases) {
     if (!e || e->mega_grid <= 0) {
         set_error("persistent decode kernel not active");
         return -1;
     }
-    const size_t n = static_cast<size_t>(2) * e->mega_nph * 8;
+    const size_t n = static_cast<size_t>(e->mega_grid) * e->mega_nph * 8;
     if (!e->mega_tl) {
         VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->mega_tl), n * 8));
         VCB_CUDA_OK(cudaMemset(e->mega_tl, 0, n * 8));

@@ -41,6 +41,8 @@ static constexpr int MG_BSLOT = 8192;          // 64 rows (32 hi + 32 lo) x 64 k
 static constexpr int MG_NACC = 4;              // TMEM accumulator stages
 static constexpr int MG_HD = 128;
 static constexpr int MG_PAGE = 64;
+static constexpr int MG_NPB = 32;              // attention: units per merge batch
+static constexpr int MG_PSTR = 132;            // floats per page partial: acc[128], m, l, pad
 
 struct MegaSmem {
     static constexpr int RING = 0;                                  // ns slots, then the B ring (attention scratch aliases it)
@@ -48,12 +50,14 @@ struct MegaSmem {
     static constexpr int NBAR = 2 * MG_NS_MAX + 2 * MG_NB_MAX + 2 * MG_NACC;
     static constexpr int MISC = BAR + NBAR * 8;                    // tmem slot, flags, producer progress, page-count table
     static constexpr int TOTAL = MISC + 32 + 34 * 4 + 64;
-    // attention scratch inside BRING
-    static constexpr int A_SC = 0;                                  // scores, double buffered: 2 x 64 floats
-    static constexpr int A_PW = 512;                                // per-warp probabilities: 8 x 64 floats
-    static constexpr int A_RED = A_PW + 8 * MG_PAGE * 4;            // per-warp partial outputs: 8 x 128 floats
+    // attention scratch, aliased onto the B ring (idle during an attention phase)
+    static constexpr int A_PART = 0;                                // page partials [MG_NPB + 1][MG_PSTR] floats (+1: carry)
+    static constexpr int A_SCW = A_PART + (MG_NPB + 1) * MG_PSTR * 4;   // per-warp scores [8][64]
+    static constexpr int A_PWW = A_SCW + 8 * MG_PAGE * 4;           // per-warp probabilities [8][64]
+    static constexpr int A_ITEM = A_PWW + 8 * MG_PAGE * 4;          // merged item: o[128], m, l
+    static constexpr int A_END = A_ITEM + MG_PSTR * 4;
 };
-static_assert(MegaSmem::A_RED + 8 * MG_HD * 4 <= 2 * MG_BSLOT, "attention scratch must fit two B slots");
+static_assert(MegaSmem::A_END <= 3 * MG_BSLOT, "attention scratch must fit three B slots (nb >= 3)");
 static_assert(MegaSmem::TOTAL <= 232448, "shared memory budget of one CTA per SM");
 
 __device__ __forceinline__ unsigned int mg_ld_acquire(const unsigned int* p) {
@@ -92,17 +96,24 @@ __device__ __forceinline__ void mg_wait(uint64_t* bar, uint32_t parity, unsigned
         }
     }
 }
-// bounded wait for a phase completion counter
+// Bounded wait for a phase completion counter.  The spin uses relaxed (L1-bypassing) loads and ONE acquire fence at the
+// end: an ld.acquire.gpu in the loop invalidates the SM's L1 on every iteration (CCTL.IVALL), which turned every
+// descriptor / bias read of the epilogue warps on the same SM into an L2 round trip (measured: ~18 us per phase).
 __device__ __forceinline__ void mg_wait_flag(const unsigned int* flag, unsigned int target, unsigned int* dbg, unsigned int role,
                                              unsigned int phase) {
     unsigned long long t0 = 0;
-    for (unsigned int spins = 0; mg_ld_acquire(flag) < target; ++spins) {
+    for (unsigned int spins = 0;; ++spins) {
+        unsigned int v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= target) break;
+        __nanosleep(32);
         if ((spins & 0x3ffu) == 0x3ffu) {
             const unsigned long long t = mg_now();
             if (t0 == 0) t0 = t;
             else if (t - t0 > 2000000000ull) mg_die(dbg, role, phase, 0x200u);
         }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void mg_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -117,10 +128,9 @@ __device__ __forceinline__ void mg_range(long long T, int c, int Ge, int& b0, in
     b0 = static_cast<int>(T * c / Ge);
     b1 = static_cast<int>(T * (c + 1) / Ge);
 }
-// debug timeline: CTA 0 and the last CTA record %globaltimer at fixed (phase, event) slots
+// debug timeline: every CTA records %globaltimer at fixed (cta, phase, event) slots
 __device__ __forceinline__ void mg_tl(const MegaArgs& A, int p, int ev) {
-    if (A.tl != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-        A.tl[(static_cast<size_t>(blockIdx.x == 0 ? 0 : 1) * A.nph + p) * 8 + ev] = mg_now();
+    if (A.tl != nullptr) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 8 + ev] = mg_now();
 }
 __device__ __forceinline__ int mg_owner(long long u, long long T, int G) { return static_cast<int>(((u + 1) * G - 1) / T); }
 
@@ -608,7 +618,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
         const int wq = wtid >> 5;                        // worker warp 0..7
         const int q = warp & 3;                          // TMEM lane quarter this warp may read
         const int grp = wq >> 2;                         // which half of the rows in the TMEM read-out
-        uint32_t it = 0, seg = 0, pgc = 0;
+        uint32_t it = 0, seg = 0;
         for (int p = 0; p < A.nph; ++p) {
             const MegaPhase& P = ph[p];
             if (P.type == MEGA_GEMM) {
@@ -654,22 +664,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     float* pdst = A.part + (static_cast<size_t>(cta) * MEGA_MAXSEG + (tile - first_tile)) * BPAD * 128 + ml;
 #pragma unroll
                     for (int j = 0; j < HB; ++j) __stcg(pdst + (grp * HB + j) * 128, v[j]);
-                    __threadfence();
+                    // release: the block barrier orders every worker's stores before thread 0's GPU-scope fence (fences are
+                    // cumulative), the atomic publishes; acquire: thread 0's fence after the atomic, then the barrier
                     mg_bar_workers();
                     const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, Ge);
                     const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, Ge);
                     const int ncontrib = c_last - c_first + 1;
-                    if (wtid == 0) *s_flag = (atomicAdd(A.tile_cnt + p * A.tile_cnt_stride + tile, 1) == ncontrib - 1);
+                    if (wtid == 0) {
+                        __threadfence();
+                        *s_flag = (atomicAdd(A.tile_cnt + p * A.tile_cnt_stride + tile, 1) == ncontrib - 1);
+                        __threadfence();
+                    }
                     mg_bar_workers();
                     if (*s_flag) {
-                        __threadfence();
                         mg_tile_epilogue<BPAD>(A, P, p, tile, c_first, ncontrib, T, Ge, wq, lane);
-                        __threadfence();
                         mg_bar_workers();
                         if (wtid == 0) {
                             A.tile_cnt[p * A.tile_cnt_stride + tile] = 0;
-                            mg_fence_proxy_async();
                             __threadfence();
+                            mg_fence_proxy_async();
                             atomicAdd(A.flags + p, 1u);
                             mg_tl(A, p, 2);
                         }
@@ -680,69 +693,80 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 }
             } else {
                 // ===== attention: units [u0, u1) ========================================================================
-                constexpr int LPT = MG_HD / 8, TPW = 32 / LPT, DPT = MG_HD / 32, KPW = MG_PAGE / 8;
-                float* sc_all = reinterpret_cast<float*>(bring + L::A_SC);
-                float* pw = reinterpret_cast<float*>(bring + L::A_PW);
-                float* red = reinterpret_cast<float*>(bring + L::A_RED);
+                // One WARP per (row, head, page) unit: scores, softmax and PV of a 64-key page need no other warp, so the 8
+                // worker warps run 8 pages concurrently and never meet at a block barrier inside a page.  A page yields an
+                // independent partial (acc[128], m, l); per batch of MG_NPB units the partials of each (row, head) item are merged
+                // in page order (one extra "carry" slot holds an item that continues into the next batch), then the item goes
+                // out directly (whole item in this CTA) or through the cross-CTA merge.
+                constexpr int LPT = MG_HD / 8, DPT = MG_HD / 32;
+                float* part_sm = reinterpret_cast<float*>(bring + L::A_PART);        // [MG_NPB + 1][MG_PSTR]
+                float* scw = reinterpret_cast<float*>(bring + L::A_SCW) + wq * MG_PAGE;
+                float* pww = reinterpret_cast<float*>(bring + L::A_PWW) + wq * MG_PAGE;
+                float* item_sm = reinterpret_cast<float*>(bring + L::A_ITEM);         // merged item: o[128], m, l
                 if (P.dep_target > 0) {
                     if (lane == 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 5, p);
                     __syncwarp();
                 }
                 if (wtid == 0) mg_tl(A, p, 4);
                 const int sub = lane % LPT;
-                int r = 0;
-                while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u0) ++r;
-                int npg = s_cum[r + 1] - s_cum[r];
-                int rem = u0 - A.H * s_cum[r];
-                int h = npg ? rem / npg : 0, pg = npg ? rem - h * npg : 0;
-                int u = u0;
-                while (u < u1) {
-                    const int pa = pg, pb = min(npg, pa + (u1 - u));
-                    const int pos = A.row_pos[r];
-                    const bool has_self = pb == npg;                       // the page holding the current position
-                    const int rh = r * A.H + h;
-                    float qv[8], kself[8], vself[DPT];
-                    {
-                        const float4* qp = reinterpret_cast<const float4*>(A.qbuf + static_cast<size_t>(rh) * MG_HD + sub * 8);
-                        const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
-                        qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w;
-                        qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-                    }
+                const uint32_t it0 = it;
+                // unit -> (row, head, page)
+                auto locate = [&](int u, int& r, int& h, int& pg, int& npg) {
+                    r = 0;
+                    while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u) ++r;
+                    npg = s_cum[r + 1] - s_cum[r];
+                    const int rem = u - A.H * s_cum[r];
+                    h = rem / npg;
+                    pg = rem - h * npg;
+                };
+                int carry_rh = -1;                                                  // item continued from the previous batch
+                for (int ub = u0; ub < u1; ub += MG_NPB) {
+                    const int ue = min(u1, ub + MG_NPB);
+                    // ---- (1) pages: warp wq takes units ub + wq, ub + wq + 8, ... -------------------------------------------------
+                    for (int u = ub + wq; u < ue; u += 8) {
+                        int r, h, pgi, npg;
+                        locate(u, r, h, pgi, npg);
+                        const int pos = A.row_pos[r];
+                        const int rh = r * A.H + h;
+                        const uint32_t itu = it0 + static_cast<uint32_t>(u - u0) * 2 * NSL;
+                        float qv[8];
+                        {
+                            const float4* qp = reinterpret_cast<const float4*>(A.qbuf + static_cast<size_t>(rh) * MG_HD + sub * 8);
+                            const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
+                            qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w;
+                            qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+                        }
+                        const bool self_page = pgi == npg - 1;                      // holds the current position
+                        const int self_t = self_page ? pos - pgi * MG_PAGE : -1;
+                        float kself[8], vself[DPT];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) kself[i] = 0.f;
+                        for (int i = 0; i < 8; ++i) kself[i] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < DPT; ++i) vself[i] = 0.f;
-                    if (has_self) {
-                        const float4* kp = reinterpret_cast<const float4*>(A.knew + static_cast<size_t>(rh) * MG_HD + sub * 8);
-                        const float4 k0 = __ldcg(kp), k1 = __ldcg(kp + 1);
-                        kself[0] = k0.x; kself[1] = k0.y; kself[2] = k0.z; kself[3] = k0.w;
-                        kself[4] = k1.x; kself[5] = k1.y; kself[6] = k1.z; kself[7] = k1.w;
-                        const float4 v0 = __ldcg(reinterpret_cast<const float4*>(A.vnew + static_cast<size_t>(rh) * MG_HD + lane * DPT));
-                        vself[0] = v0.x; vself[1] = v0.y; vself[2] = v0.z; vself[3] = v0.w;
-                    }
-                    float m_run = -INFINITY, l_run = 0.f;
-                    float acc[DPT];
-#pragma unroll
-                    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
-                    for (int pgi = pa; pgi < pb; ++pgi, ++pgc) {
-                        // ring items of this page: NSL K slots then NSL V slots
+                        for (int i = 0; i < DPT; ++i) vself[i] = 0.f;
+                        if (self_page) {
+                            const float4* kp = reinterpret_cast<const float4*>(A.knew + static_cast<size_t>(rh) * MG_HD + sub * 8);
+                            const float4 k0 = __ldcg(kp), k1 = __ldcg(kp + 1);
+                            kself[0] = k0.x; kself[1] = k0.y; kself[2] = k0.z; kself[3] = k0.w;
+                            kself[4] = k1.x; kself[5] = k1.y; kself[6] = k1.z; kself[7] = k1.w;
+                            const float4 v0 = __ldcg(reinterpret_cast<const float4*>(A.vnew + static_cast<size_t>(rh) * MG_HD + lane * DPT));
+                            vself[0] = v0.x; vself[1] = v0.y; vself[2] = v0.z; vself[3] = v0.w;
+                        }
                         uint32_t ks[NSL], vs[NSL];
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) {
-                            ks[j] = (it + j) % MG_NS;
-                            vs[j] = (it + NSL + j) % MG_NS;
+                            ks[j] = (itu + j) % MG_NS;
+                            vs[j] = (itu + NSL + j) % MG_NS;
                         }
 #pragma unroll
-                        for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((it + j) / MG_NS) & 1, A.dbg, 6, p);
-                        float* sc = sc_all + (pgc & 1) * MG_PAGE;
-#pragma unroll
-                        for (int itq = 0; itq < KPW / TPW; ++itq) {
-                            const int t = wq * KPW + itq * TPW + lane / LPT;
-                            const int tg = pgi * MG_PAGE + t;
+                        for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((itu + j) / MG_NS) & 1, A.dbg, 6, p);
+                        // scores: 2 keys per iteration (16 lanes x 8 dims each), xor-shuffle reduce
+#pragma unroll 4
+                        for (int kk = 0; kk < MG_PAGE / 2; ++kk) {
+                            const int t = 2 * kk + lane / LPT;
                             float kvv[8];
                             const KVT* Kp = reinterpret_cast<const KVT*>(ring + ks[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + sub * 8;
                             mg_load_kv<KVT, 8>(Kp, kvv);
-                            if (tg == pos) {
+                            if (t == self_t) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) kvv[i] = kself[i];
                             }
@@ -751,36 +775,32 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             for (int i = 0; i < 8; ++i) dsum = fmaf(qv[i], kvv[i], dsum);
 #pragma unroll
                             for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-                            if (sub == 0) sc[t] = (tg <= pos) ? dsum * A.scale : -INFINITY;
+                            if (sub == 0) scw[t] = (pgi * MG_PAGE + t <= pos) ? dsum * A.scale : -INFINITY;
                         }
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane < 8) {
 #pragma unroll
-                            for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[ks[j]]);
+                            for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[ks[j]]);       // 8 arrivals release the slot
                         }
-                        mg_bar_workers();
-                        const float s0 = sc[lane], s1 = sc[lane + 32];
-                        const float m_new = fmaxf(m_run, warp_max(fmaxf(s0, s1)));
-                        const float corr = expf(m_run - m_new);
-                        const float e0 = expf(s0 - m_new), e1 = expf(s1 - m_new);
-                        float* mypw = pw + wq * MG_PAGE;
-                        mypw[lane] = e0;
-                        mypw[lane + 32] = e1;
-                        l_run = l_run * corr + warp_sum(e0 + e1);
-                        m_run = m_new;
+                        const float s0 = scw[lane], s1 = scw[lane + 32];
+                        const float m_pg = warp_max(fmaxf(s0, s1));                 // finite: key 0 of page 0 / the self key is live
+                        const float e0 = expf(s0 - m_pg), e1 = expf(s1 - m_pg);
+                        pww[lane] = e0;
+                        pww[lane + 32] = e1;
+                        const float l_pg = warp_sum(e0 + e1);
                         __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((it + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
+                        for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((itu + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
+                        float acc[DPT];
 #pragma unroll
-                        for (int i = 0; i < DPT; ++i) acc[i] *= corr;
-#pragma unroll
-                        for (int tt = 0; tt < KPW; ++tt) {
-                            const int t = wq * KPW + tt;
-                            const float pt_ = mypw[t];
+                        for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+#pragma unroll 8
+                        for (int t = 0; t < MG_PAGE; ++t) {
+                            const float pt_ = pww[t];
                             float vv[DPT];
                             const KVT* Vp = reinterpret_cast<const KVT*>(ring + vs[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + lane * DPT;
                             mg_load_kv<KVT, DPT>(Vp, vv);
-                            if (pgi * MG_PAGE + t == pos) {
+                            if (t == self_t) {
 #pragma unroll
                                 for (int i = 0; i < DPT; ++i) vv[i] = vself[i];
                             }
@@ -788,85 +808,114 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
                         }
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane < 8) {
 #pragma unroll
                             for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[vs[j]]);
                         }
-                        it += 2 * NSL;
+                        float* ps = part_sm + (u - ub) * MG_PSTR;
+                        *reinterpret_cast<float4*>(ps + lane * DPT) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        if (lane == 0) {
+                            ps[MG_HD] = m_pg;
+                            ps[MG_HD + 1] = l_pg;
+                        }
                     }
-                    // ---- combine the 8 warps' partial outputs of this item segment -------------------------------------------------
-#pragma unroll
-                    for (int i = 0; i < DPT; ++i) red[wq * MG_HD + lane * DPT + i] = acc[i];
                     mg_bar_workers();
-                    const size_t ocol = static_cast<size_t>(h) * MG_HD;
-                    if (pa == 0 && pb == npg) {
-                        if (wtid < MG_HD) {
-                            float osum = 0.f;
-#pragma unroll
-                            for (int w = 0; w < 8; ++w) osum += red[w * MG_HD + wtid];
-                            const float o = osum / l_run;
-                            __nv_bfloat16 hi, lo;
-                            split_bf16(o, hi, lo);
-                            A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                            A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
-                        }
-                        mg_bar_workers();
-                    } else {
-                        // item shared with neighbouring CTAs: publish (o, m, l); the last arriver merges in CTA order
+                    // ---- (2) fold the batch's page partials per item -------------------------------------------------------------
+                    // Canonical result: an item's output is the left fold of its page partials in page order,
+                    //   (O, M, L) <- (O e^{M-M'} + a_p e^{m_p-M'}, M' = max(M, m_p), L e^{M-M'} + l_p e^{m_p-M'}),
+                    // no matter which warp or CTA computed a page -- so a row's tokens do not depend on what else is in the batch.
+                    // Items inside this CTA's range fold in shared memory (the carry slot continues across batches); items shared
+                    // with neighbouring CTAs publish their page partials, and the last CTA to arrive folds all pages.
+                    int u = ub;
+                    while (u < ue) {
+                        int r, h, pg, npg;
+                        locate(u, r, h, pg, npg);
+                        const int rh = r * A.H + h;
+                        const int gb = min(ue, u + (npg - pg));                     // units [u, gb) belong to this item
+                        const int pb = pg + (gb - u);                               // one past the last page of this piece
                         const long long ui0 = static_cast<long long>(A.H) * s_cum[r] + static_cast<long long>(h) * npg;
-                        const int c_first = mg_owner(ui0, U, Ue), c_last = mg_owner(ui0 + npg - 1, U, Ue);
-                        const int nch = c_last - c_first + 1;
-                        float* base = A.att_ws + static_cast<size_t>(rh) * MEGA_ATT_MAXC * (MG_HD + 2);
-                        float* myws = base + static_cast<size_t>(cta - c_first) * (MG_HD + 2);
-                        if (wtid < MG_HD) {
-                            float osum = 0.f;
-#pragma unroll
-                            for (int w = 0; w < 8; ++w) osum += red[w * MG_HD + wtid];
-                            __stcg(myws + wtid, osum);
-                        }
-                        if (wtid == 0) {
-                            __stcg(myws + MG_HD, m_run);
-                            __stcg(myws + MG_HD + 1, l_run);
-                        }
-                        __threadfence();
-                        mg_bar_workers();
-                        if (wtid == 0) *s_flag = (atomicAdd(A.att_cnt + rh, 1) == nch - 1);
-                        mg_bar_workers();
-                        if (*s_flag) {
-                            __threadfence();
+                        const bool spans = ui0 < u0 || ui0 + npg > u1;              // item shared with other CTAs
+                        const bool more = (gb == ue) && (ue < u1) && (pb < npg);    // continues in this CTA's next batch
+                        const size_t ocol = static_cast<size_t>(h) * MG_HD;
+                        if (!spans) {
                             if (wtid < MG_HD) {
-                                float M = -INFINITY;
-                                for (int c = 0; c < nch; ++c) M = fmaxf(M, __ldcg(base + c * (MG_HD + 2) + MG_HD));
-                                float Lsum = 0.f, O = 0.f;
-                                for (int c = 0; c < nch; ++c) {
-                                    const float w = expf(__ldcg(base + c * (MG_HD + 2) + MG_HD) - M);
-                                    Lsum += __ldcg(base + c * (MG_HD + 2) + MG_HD + 1) * w;
-                                    O += __ldcg(base + c * (MG_HD + 2) + wtid) * w;
+                                const bool cont_in = carry_rh == rh;
+                                float M = cont_in ? part_sm[MG_NPB * MG_PSTR + MG_HD] : -INFINITY;
+                                float Ls = cont_in ? part_sm[MG_NPB * MG_PSTR + MG_HD + 1] : 0.f;
+                                float O = cont_in ? part_sm[MG_NPB * MG_PSTR + wtid] : 0.f;
+                                for (int j = u; j < gb; ++j) {
+                                    const float* ps = part_sm + (j - ub) * MG_PSTR;
+                                    const float mp = ps[MG_HD], Mn = fmaxf(M, mp);
+                                    const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
+                                    Ls = Ls * c1 + ps[MG_HD + 1] * c2;
+                                    O = O * c1 + ps[wtid] * c2;
+                                    M = Mn;
                                 }
-                                const float o = O / Lsum;
-                                __nv_bfloat16 hi, lo;
-                                split_bf16(o, hi, lo);
-                                A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                                A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                                if (more) {
+                                    item_sm[wtid] = O;
+                                    if (wtid == 0) {
+                                        item_sm[MG_HD] = M;
+                                        item_sm[MG_HD + 1] = Ls;
+                                    }
+                                } else {
+                                    const float o = O / Ls;
+                                    __nv_bfloat16 hi, lo;
+                                    split_bf16(o, hi, lo);
+                                    A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                                    A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                                }
                             }
-                            if (wtid == 0) A.att_cnt[rh] = 0;
+                            mg_bar_workers();
+                            if (more) {
+                                if (wtid < MG_HD + 2) part_sm[MG_NPB * MG_PSTR + wtid] = item_sm[wtid];
+                                carry_rh = rh;
+                            } else {
+                                carry_rh = -1;
+                            }
+                        } else {
+                            float* wsi = A.att_ws + static_cast<size_t>(rh) * A.max_pages * MG_PSTR;
+                            for (int i = wtid; i < (gb - u) * (MG_HD + 2); i += MG_WORKERS) {
+                                const int j = i / (MG_HD + 2), e = i - j * (MG_HD + 2);
+                                __stcg(wsi + static_cast<size_t>(pg + j) * MG_PSTR + e, part_sm[(u - ub + j) * MG_PSTR + e]);
+                            }
+                            if (!more) {
+                                // my last piece of this item: publish, count; the last CTA folds pages 0 .. npg-1
+                                const int c_first = mg_owner(ui0, U, Ue), c_last = mg_owner(ui0 + npg - 1, U, Ue);
+                                const int nch = c_last - c_first + 1;
+                                mg_bar_workers();
+                                if (wtid == 0) {
+                                    __threadfence();
+                                    *s_flag = (atomicAdd(A.att_cnt + rh, 1) == nch - 1);
+                                    __threadfence();
+                                }
+                                mg_bar_workers();
+                                if (*s_flag) {
+                                    if (wtid < MG_HD) {
+                                        float M = -INFINITY, Ls = 0.f, O = 0.f;
+                                        for (int j = 0; j < npg; ++j) {
+                                            const float* ps = wsi + static_cast<size_t>(j) * MG_PSTR;
+                                            const float mp = __ldcg(ps + MG_HD), Mn = fmaxf(M, mp);
+                                            const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
+                                            Ls = Ls * c1 + __ldcg(ps + MG_HD + 1) * c2;
+                                            O = O * c1 + __ldcg(ps + wtid) * c2;
+                                            M = Mn;
+                                        }
+                                        const float o = O / Ls;
+                                        __nv_bfloat16 hi, lo;
+                                        split_bf16(o, hi, lo);
+                                        A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                                        A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                                    }
+                                    if (wtid == 0) A.att_cnt[rh] = 0;
+                                }
+                            }
+                            carry_rh = -1;
                         }
-                        mg_bar_workers();
-                    }
-                    // ---- next item ----------------------------------------------------------------------------------------------------
-                    u += pb - pa;
-                    pg = pb;
-                    if (pg == npg) {
-                        pg = 0;
-                        if (++h == A.H) {
-                            h = 0;
-                            do {
-                                ++r;
-                                npg = r < 32 ? s_cum[r + 1] - s_cum[r] : 1;
-                            } while (r < 32 && npg == 0);
-                        }
+                        mg_bar_workers();                                           // partial slots / item_sm / s_flag are reused
+                        u = gb;
                     }
                 }
+                it = it0 + static_cast<uint32_t>(u1 - u0) * 2 * NSL;
                 // this CTA's share of the phase is done (merged outputs are counted by whoever merged them)
                 if (wtid == 0) mg_tl(A, p, 5);
                 __threadfence();

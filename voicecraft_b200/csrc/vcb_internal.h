@@ -104,7 +104,7 @@ struct MegaArgs {
     const float* knew = nullptr;
     const float* vnew = nullptr;
     __nv_bfloat16* att_out = nullptr;   // act_d (hi/lo rows)
-    float* att_ws = nullptr;            // [rows*H][MEGA_ATT_MAXC][hd+2]
+    float* att_ws = nullptr;            // [rows*H][max_pages][132]: page partials (acc[128], m, l) of items shared between CTAs
     int* att_cnt = nullptr;             // [nph? no: rows*H] arrival counters (self-resetting)
     const int* row_pos = nullptr;
     const int* row_pages = nullptr;
