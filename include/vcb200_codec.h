@@ -1,4 +1,4 @@
-/* vcb200_codec.h -- C ABI of the EnCodec token -> waveform decoder in libvcb200.so.
+/* vcb200_codec.h -- C ABI of the EnCodec decoder (token -> waveform) and encoder (waveform -> token) in libvcb200.so.
  *
  * Replaces AudioTokenizer.decode (reference data/tokenizer.py:131-133), i.e. audiocraft's
  * EncodecModel.decode = ResidualVectorQuantizer.decode + SEANetDecoder, with hand-written sm_100a kernels
@@ -39,6 +39,11 @@ int enc_load_weight(enc_engine* e, const char* name, const float* data, const in
 int enc_finalize(enc_engine* e);
 /* codes [B][n_q][T] int64 (device) -> wav [B][channels][T * hop] fp32 (device) */
 int enc_decode(enc_engine* e, const int64_t* codes_dev, float* wav_dev, int32_t B, int32_t T, void* stream);
+/* wav [B][channels][N] fp32 (device) -> codes [B][n_q][T] int64 (device), T = N down-sampled by every ratio (rounded up).
+ * Replaces AudioTokenizer.encode (reference data/tokenizer.py:127-129 -> audiocraft EncodecModel.encode = SEANetEncoder +
+ * ResidualVectorQuantizer.encode).  Needs the "enc.*" weights: "enc.conv_in.weight", "enc.down{i}.res{j}.conv1.weight",
+ * "enc.down{i}.conv.weight" (strided), "enc.lstm.*", "enc.conv_out.weight". */
+int enc_encode(enc_engine* e, const float* wav_dev, int64_t* codes_dev, int32_t B, int32_t N, void* stream);
 int64_t enc_counter(enc_engine* e, const char* name); /* "launches", "hop", "flops_per_frame" */
 
 #ifdef __cplusplus

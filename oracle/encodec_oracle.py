@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- torch-CPU fp32 restatement of EnCodec token -> waveform decode.
+"""TEST INFRASTRUCTURE ONLY -- torch-CPU fp32 restatement of EnCodec token -> waveform decode (and, for SURVEY.md
+section 8f row f1, of the waveform -> token encode: SEANetEncoder + ResidualVectorQuantizer.encode, data/tokenizer.py:127-129).
 
 The reference calls ``audiocraft`` (facebookresearch/audiocraft @ c5157b5bf14bf83449c17ea1eeb66c19fb4bc7f0,
 un-vendored, NOT installable offline) at data/tokenizer.py:109-110 (model load) and :131-133
@@ -84,11 +85,56 @@ def weight_shapes(cfg):
     return shp
 
 
-def make_state_dict(cfg, seed=0):
-    """Deterministic random weights (CPU generator) scaled so activations stay O(1) through the stack."""
+def encoder_plan(cfg):
+    """SEANetEncoder (audiocraft modules/seanet.py): conv k7 -> per ratio (reversed) [ResBlock x n, ELU, Conv1d(k=2r, stride r)]
+    -> LSTM + skip -> ELU -> conv k7 (-> dimension)."""
+    plan = [dict(kind="conv", name="enc.conv_in", cin=cfg.channels, cout=cfg.n_filters, k=cfg.kernel_size, stride=1, elu_in=False)]
+    ch = cfg.n_filters
+    for i, r in enumerate(reversed(cfg.ratios)):
+        for j in range(cfg.n_residual_layers):
+            plan.append(dict(kind="res", name=f"enc.down{i}.res{j}", dim=ch, hidden=ch // cfg.compress,
+                             k=cfg.residual_kernel_size, dil=cfg.dilation_base ** j, true_skip=cfg.true_skip))
+        plan.append(dict(kind="conv", name=f"enc.down{i}.conv", cin=ch, cout=2 * ch, k=2 * r, stride=r, elu_in=True))
+        ch *= 2
+    if cfg.lstm:
+        plan.append(dict(kind="lstm", name="enc.lstm", dim=ch, layers=cfg.lstm))
+    plan.append(dict(kind="conv", name="enc.conv_out", cin=ch, cout=cfg.dimension, k=cfg.last_kernel_size, stride=1, elu_in=True))
+    return plan
+
+
+def encoder_weight_shapes(cfg):
+    shp = {}
+    for L in encoder_plan(cfg):
+        n = L["name"]
+        if L["kind"] == "conv":
+            shp[n + ".weight"] = (L["cout"], L["cin"], L["k"])
+            shp[n + ".bias"] = (L["cout"],)
+        elif L["kind"] == "lstm":
+            for l in range(L["layers"]):
+                shp[f"{n}.weight_ih_l{l}"] = (4 * L["dim"], L["dim"])
+                shp[f"{n}.weight_hh_l{l}"] = (4 * L["dim"], L["dim"])
+                shp[f"{n}.bias_ih_l{l}"] = (4 * L["dim"],)
+                shp[f"{n}.bias_hh_l{l}"] = (4 * L["dim"],)
+        else:
+            shp[n + ".conv1.weight"] = (L["hidden"], L["dim"], L["k"])
+            shp[n + ".conv1.bias"] = (L["hidden"],)
+            shp[n + ".conv2.weight"] = (L["dim"], L["hidden"], 1)
+            shp[n + ".conv2.bias"] = (L["dim"],)
+            if not L["true_skip"]:
+                shp[n + ".shortcut.weight"] = (L["dim"], L["dim"], 1)
+                shp[n + ".shortcut.bias"] = (L["dim"],)
+    return shp
+
+
+def make_state_dict(cfg, seed=0, encoder=False):
+    """Deterministic random weights (CPU generator) scaled so activations stay O(1) through the stack.  The encoder's
+    weights (encoder=True) are drawn AFTER the decoder's, so decoder fixtures do not depend on the flag."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd = {}
-    for name, shape in weight_shapes(cfg).items():
+    shapes = dict(weight_shapes(cfg))
+    if encoder:
+        shapes.update(encoder_weight_shapes(cfg))
+    for name, shape in shapes.items():
         if name.endswith("embed"):
             sd[name] = torch.randn(*shape, generator=g) * 0.5
         elif name.endswith("bias") or "bias_" in name:
@@ -115,16 +161,20 @@ def _pad1d(x, left, right, mode):
     return y[..., : y.shape[-1] - extra]
 
 
-def conv1d(cfg, x, w, b, dil=1):
-    """StreamableConv1d with stride 1 (the only stride in the decoder): pad, then plain conv."""
-    k = w.shape[-1]
-    total = (k - 1) * dil
+def conv1d(cfg, x, w, b, dil=1, stride=1):
+    """StreamableConv1d (audiocraft modules/conv.py): pad (k_eff - stride) in total -- causal: all on the left -- plus the
+    extra right padding that completes the last window (get_extra_padding_for_conv1d), then a plain conv."""
+    k = (w.shape[-1] - 1) * dil + 1
+    total = k - stride
+    length = x.shape[-1]
+    n_frames = (length - k + total) / stride + 1
+    extra = (math.ceil(n_frames) - 1) * stride + (k - total) - length
     if cfg.causal:
-        x = _pad1d(x, total, 0, cfg.pad_mode)
+        x = _pad1d(x, total, extra, cfg.pad_mode)
     else:
         right = total // 2
-        x = _pad1d(x, total - right, right, cfg.pad_mode)
-    return F.conv1d(x, w, b, dilation=dil)
+        x = _pad1d(x, total - right, right + extra, cfg.pad_mode)
+    return F.conv1d(x, w, b, dilation=dil, stride=stride)
 
 
 def convtr1d(cfg, x, w, b, stride):
@@ -187,6 +237,54 @@ def decode(cfg, sd, codes):
     return x
 
 
+def _res_block(cfg, x, sd, n, L):
+    h = conv1d(cfg, F.elu(x), sd[n + ".conv1.weight"], sd[n + ".conv1.bias"], L["dil"])
+    h = conv1d(cfg, F.elu(h), sd[n + ".conv2.weight"], sd[n + ".conv2.bias"], 1)
+    s = x if L["true_skip"] else conv1d(cfg, x, sd[n + ".shortcut.weight"], sd[n + ".shortcut.bias"], 1)
+    return s + h
+
+
+@torch.no_grad()
+def encode_latent(cfg, sd, wav):
+    """wav [B,channels,N] fp32 -> latent [B,dimension,T]."""
+    x = wav
+    for L in encoder_plan(cfg):
+        n = L["name"]
+        if L["kind"] == "conv":
+            x = conv1d(cfg, F.elu(x) if L["elu_in"] else x, sd[n + ".weight"], sd[n + ".bias"], 1, L["stride"])
+        elif L["kind"] == "lstm":
+            x = lstm(x.permute(2, 0, 1), sd, n, L["layers"]).permute(1, 2, 0)
+        else:
+            x = _res_block(cfg, x, sd, n, L)
+    return x
+
+
+@torch.no_grad()
+def rvq_encode(cfg, sd, z, return_gaps=False):
+    """ResidualVectorQuantizer.encode (audiocraft quantization/core_vq.py): per stage, nearest code in Euclidean distance
+    (dist = -(|x|^2 - 2 x.e + |e|^2), arg max), then subtract it.  z [B,D,T] -> codes [B,K,T] (+ per decision, the gap
+    between the two best distances: a fp32 implementation may legitimately differ only where it is ~1e-6 relative)."""
+    B, D, T = z.shape
+    resid = z.transpose(1, 2).reshape(B * T, D)
+    codes, gaps = [], []
+    for q in range(cfg.n_q):
+        emb = sd[f"vq.{q}.embed"]
+        dist = -(resid.pow(2).sum(1, keepdim=True) - 2 * resid @ emb.t() + emb.pow(2).sum(1)[None])
+        top2 = dist.topk(2, dim=-1)
+        idx = top2.indices[:, 0]
+        gaps.append((top2.values[:, 0] - top2.values[:, 1]).view(B, T))
+        codes.append(idx.view(B, T))
+        resid = resid - F.embedding(idx, emb)
+    codes = torch.stack(codes, dim=1)
+    return (codes, torch.stack(gaps, dim=1)) if return_gaps else codes
+
+
+@torch.no_grad()
+def encode(cfg, sd, wav):
+    """wav [B,channels,N] fp32 -> codes [B,K,T] int64   (EncodecModel.encode)."""
+    return rvq_encode(cfg, sd, encode_latent(cfg, sd, wav))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # bridge to the transformers twin (used only by tests/golden/make_golden_codec.py in the build container)
 # ----------------------------------------------------------------------------------------------------------------
@@ -238,4 +336,30 @@ def to_hf_model(cfg, sd):
                 if not L["true_skip"]:
                     set_conv(blk.shortcut, sd[n + ".shortcut.weight"], sd[n + ".shortcut.bias"])
                 idx += 1
+        if "enc.conv_in.weight" in sd:
+            layers = list(m.encoder.layers)
+            idx = 0
+            for L in encoder_plan(cfg):
+                n = L["name"]
+                if L["kind"] == "conv":
+                    while not hasattr(layers[idx], "conv"):
+                        idx += 1
+                    set_conv(layers[idx], sd[n + ".weight"], sd[n + ".bias"])
+                    idx += 1
+                elif L["kind"] == "lstm":
+                    while not hasattr(layers[idx], "lstm"):
+                        idx += 1
+                    for l in range(L["layers"]):
+                        for part in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                            getattr(layers[idx].lstm, f"{part}_l{l}").copy_(sd[f"{n}.{part}_l{l}"])
+                    idx += 1
+                else:
+                    while not hasattr(layers[idx], "block"):
+                        idx += 1
+                    blk = layers[idx]
+                    set_conv(blk.block[1], sd[n + ".conv1.weight"], sd[n + ".conv1.bias"])
+                    set_conv(blk.block[3], sd[n + ".conv2.weight"], sd[n + ".conv2.bias"])
+                    if not L["true_skip"]:
+                        set_conv(blk.shortcut, sd[n + ".shortcut.weight"], sd[n + ".shortcut.bias"])
+                    idx += 1
     return m

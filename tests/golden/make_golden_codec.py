@@ -42,6 +42,36 @@ def main():
     np.savez_compressed(os.path.join(HERE, "codec.npz"), **out)
     print("codec goldens written")
 
+    # ---- encode direction: wav -> codes through the twin's encoder + RVQ ------------------
+    enc = {}
+    for name, (over, B, T, seed) in CASES.items():
+        cfg = eo.default_config(**over)
+        sd = eo.make_state_dict(cfg, seed=seed, encoder=True)
+        hop = int(np.prod(cfg.ratios))
+        g = torch.Generator().manual_seed(200 + seed)
+        N = T * hop - (37 if name == "mid_default" else 0)          # one ragged length: exercises the extra right padding
+        wav = torch.randn(B, cfg.channels, N, generator=g) * 0.3
+        z = eo.encode_latent(cfg, sd, wav)
+        codes, gaps = eo.rvq_encode(cfg, sd, z, return_gaps=True)
+        hf = eo.to_hf_model(cfg, sd)
+        with torch.no_grad():
+            zr = hf.encoder(wav)
+            ref = hf.encode(wav, bandwidth=hf.config.target_bandwidths[0]).audio_codes[0]
+        err = float((zr - z).abs().max())
+        same = float((ref == codes).float().mean())
+        # a code may differ from the twin's only where the two nearest codes are (numerically) equidistant
+        bad = (ref != codes)
+        assert err < 2e-5 and ref.shape == codes.shape
+        assert (not bad.any()) or float(gaps[bad].max()) < 1e-4, (same, float(gaps[bad].max()))
+        print(f"{name}: wav {tuple(wav.shape)} -> codes {tuple(codes.shape)}, max|latent - twin| = {err:.3g}, codes equal {same:.4f}, "
+              f"min decision gap {float(gaps.min()):.3g}")
+        enc[f"{name}.wav"] = wav.numpy()
+        enc[f"{name}.latent"] = zr.numpy()
+        enc[f"{name}.codes"] = ref.numpy()
+        enc[f"{name}.gaps"] = gaps.numpy()
+    np.savez_compressed(os.path.join(HERE, "codec_encode.npz"), **enc)
+    print("codec encode goldens written")
+
 
 if __name__ == "__main__":
     main()

@@ -48,6 +48,7 @@ struct ConvArgs {
     const float* residual; // [B][Cout][Tout] or null
     int Cin, Cout, Tin, Tout, ks, dil, padL, reflect, elu_in;
     int convT, r;          // transposed conv: stride r, kernel 2r, one GEMM per phase (blockIdx.z % r)
+    int stride;            // forward conv stride (encoder down-sampling: stride r, kernel 2r); 1 in the decoder
 };
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvArgs a) {
                     } else {
                         ci = k / a.ks;
                         const int kx = k - ci * a.ks;
-                        src = n + kx * a.dil - a.padL;
+                        src = n * a.stride + kx * a.dil - a.padL;
                         ok = n < a.Tout;
                         if (ok && (src < 0 || src >= a.Tin)) {
                             if (a.reflect) src = src < 0 ? -src : 2 * (a.Tin - 1) - src;
@@ -201,6 +202,37 @@ lstm_step_kernel(const float* __restrict__ pre, const float* __restrict__ Whh, c
     }
 }
 
+// RVQ encode, one quantizer stage (audiocraft ResidualVectorQuantizer.encode / core_vq.py EuclideanCodebook.quantize):
+// scores[b][c][t] = e_c . x - |e_c|^2 / 2 come from conv_gemm_kernel (k = 1, bias = -|e|^2/2); the nearest code is their
+// argmax (first index wins), then the residual loses that code's embedding.  One thread per (b, t), coalesced over t.
+__global__ void rvq_pick_kernel(const float* __restrict__ scores, const float* __restrict__ embed, float* __restrict__ resid,
+                                long long* __restrict__ codes, int bins, int D, int T, int n_q, int q) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (t >= T) return;
+    const float* sc = scores + static_cast<size_t>(b) * bins * T + t;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int c = 0; c < bins; ++c) {
+        const float v = sc[static_cast<size_t>(c) * T];
+        if (v > best) {
+            best = v;
+            bi = c;
+        }
+    }
+    codes[(static_cast<size_t>(b) * n_q + q) * T + t] = bi;
+    float* r = resid + static_cast<size_t>(b) * D * T + t;
+    const float* e = embed + static_cast<size_t>(bi) * D;
+    for (int c = 0; c < D; ++c) r[static_cast<size_t>(c) * T] -= e[c];
+}
+
+__global__ void half_sqnorm_neg_kernel(const float* __restrict__ embed, float* __restrict__ out, int bins, int D) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= bins) return;
+    float s = 0.f;
+    for (int i = 0; i < D; ++i) s = fmaf(embed[static_cast<size_t>(c) * D + i], embed[static_cast<size_t>(c) * D + i], s);
+    out[c] = -0.5f * s;
+}
+
 // ConvTranspose1d weight [Cin][Cout][2r] -> per-phase GEMM operand [r][Cout][2*Cin]  (k = tap*Cin + ci, tap in {0,1})
 __global__ void pack_convtr_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout, int r) {
     const size_t total = static_cast<size_t>(r) * Cout * 2 * Cin;
@@ -230,7 +262,7 @@ struct enc_engine {
     std::vector<float*> owned;
     float** d_embed = nullptr;
     int hop = 1;
-    bool finalized = false;
+    bool finalized = false, has_encoder = false;
     // activation buffers for a batch chunk
     float* buf[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t buf_floats = 0;
@@ -277,6 +309,19 @@ ConvArgs conv_args(const enc_engine* e, const float* A, const float* bias, const
     a.padL = e->cfg.causal ? total : total - total / 2;
     a.reflect = e->cfg.pad_reflect;
     a.elu_in = elu_in;
+    a.stride = 1;
+    return a;
+}
+
+// Strided Conv1d of the encoder (audiocraft StreamableConv1d with stride r, kernel 2r): pad (k - stride) in total -- causal:
+// all on the left -- plus whatever the last window lacks on the right (get_extra_padding_for_conv1d); Tout = ceil(Tin / r).
+ConvArgs conv_args_strided(const enc_engine* e, const float* A, const float* bias, const float* in, float* out, int Cin, int Cout,
+                           int Tin, int ks, int stride, int elu_in) {
+    ConvArgs a = conv_args(e, A, bias, in, out, Cin, Cout, Tin, ks, 1, elu_in, nullptr);
+    const int total = ks - stride;
+    a.padL = e->cfg.causal ? total : total - total / 2;
+    a.stride = stride;
+    a.Tout = (Tin + stride - 1) / stride;
     return a;
 }
 
@@ -305,6 +350,121 @@ int ensure_buffers(enc_engine* e, int B, int T) {
     return 0;
 }
 
+// StreamableLSTM with skip over x [B, ch, T] -> y (z, pre: scratch).  side = "dec" / "enc".
+int lstm_stack(enc_engine* e, const char* side, const float* x, float* y, float* z, float* pre, int B, int ch, int T,
+               cudaStream_t st) {
+    const enc_config& c = e->cfg;
+    char nm[128];
+    const float* layer_in = x;
+    for (int l = 0; l < c.lstm; ++l) {
+        float *wih, *whh, *bsum;
+        snprintf(nm, sizeof(nm), "%s.lstm.weight_ih_l%d", side, l);
+        if (enc_need(e, nm, &wih)) return -1;
+        snprintf(nm, sizeof(nm), "%s.lstm.weight_hh_l%d", side, l);
+        if (enc_need(e, nm, &whh)) return -1;
+        snprintf(nm, sizeof(nm), "%s.lstm.__bias_sum_l%d", side, l);
+        if (enc_need(e, nm, &bsum)) return -1;
+        // pre[B, 4H, T] = W_ih * in + (b_ih + b_hh)   (a k=1 convolution, zero padding irrelevant)
+        ConvArgs a = conv_args(e, wih, bsum, layer_in, pre, ch, 4 * ch, T, 1, 1, 0, nullptr);
+        if (conv_launch(e, a, B, st)) return -1;
+        VCB_CUDA_OK(cudaMemsetAsync(e->h0, 0, static_cast<size_t>(B) * ch * 4, st));
+        VCB_CUDA_OK(cudaMemsetAsync(e->cst, 0, static_cast<size_t>(B) * ch * 4, st));
+        float* seq_out = (l == c.lstm - 1) ? y : z;
+        const float* skip = (l == c.lstm - 1) ? x : nullptr;      // y = LSTM(x) + x   (skip on the stack input)
+        float *hin = e->h0, *hout = e->h1;
+        for (int t = 0; t < T; ++t) {
+            lstm_step_kernel<<<dim3((ch + 7) / 8, (B + 3) / 4), 256, 0, st>>>(pre, whh, hin, hout, e->cst, seq_out, skip, B, ch, T, t);
+            std::swap(hin, hout);
+        }
+        VCB_CUDA_OK(cudaGetLastError());
+        e->launches += T;
+        layer_in = seq_out;
+    }
+    return 0;
+}
+
+// Residual block shared by encoder and decoder: x -> shortcut(x) + conv k1(ELU(conv k3 dil(ELU(x)))).  Result in `pre`.
+int res_block(enc_engine* e, const char* prefix, const float* x, float* y, float* z, float* pre, int B, int ch, int T, int dil,
+              cudaStream_t st) {
+    const enc_config& c = e->cfg;
+    char nm[160];
+    const int hidden = ch / c.compress;
+    float *w1, *b1, *w2, *b2;
+    snprintf(nm, sizeof(nm), "%s.conv1.weight", prefix);
+    if (enc_need(e, nm, &w1)) return -1;
+    snprintf(nm, sizeof(nm), "%s.conv1.bias", prefix);
+    if (enc_need(e, nm, &b1)) return -1;
+    snprintf(nm, sizeof(nm), "%s.conv2.weight", prefix);
+    if (enc_need(e, nm, &w2)) return -1;
+    snprintf(nm, sizeof(nm), "%s.conv2.bias", prefix);
+    if (enc_need(e, nm, &b2)) return -1;
+    if (conv_launch(e, conv_args(e, w1, b1, x, y, ch, hidden, T, c.residual_kernel_size, dil, 1, nullptr), B, st)) return -1;
+    const float* res = x;
+    if (!c.true_skip) {
+        float *ws, *bsc;
+        snprintf(nm, sizeof(nm), "%s.shortcut.weight", prefix);
+        if (enc_need(e, nm, &ws)) return -1;
+        snprintf(nm, sizeof(nm), "%s.shortcut.bias", prefix);
+        if (enc_need(e, nm, &bsc)) return -1;
+        if (conv_launch(e, conv_args(e, ws, bsc, x, z, ch, ch, T, 1, 1, 0, nullptr), B, st)) return -1;
+        res = z;
+    }
+    return conv_launch(e, conv_args(e, w2, b2, y, pre, hidden, ch, T, 1, 1, 1, res), B, st);
+}
+
+// wav [B, channels, N] -> codes [B, n_q, T]: SEANetEncoder (conv k7 -> n x [ResBlock, ELU, strided conv] -> LSTM + skip -> ELU ->
+// conv k7) and residual vector quantisation.  (reference data/tokenizer.py:127-129 -> audiocraft EncodecModel.encode)
+int encode_chunk(enc_engine* e, const float* wav, int64_t* codes, int B, int N, cudaStream_t st) {
+    const enc_config& c = e->cfg;
+    char nm[128];
+    float *x = e->buf[0], *y = e->buf[1], *z = e->buf[2], *pre = e->buf[3];
+    float *wt, *bs;
+    int ch = c.n_filters, t_cur = N;
+    if (enc_need(e, "enc.conv_in.weight", &wt) || enc_need(e, "enc.conv_in.bias", &bs)) return -1;
+    if (conv_launch(e, conv_args(e, wt, bs, wav, x, c.channels, ch, t_cur, c.kernel_size, 1, 0, nullptr), B, st)) return -1;
+    for (int i = 0; i < c.n_ratios; ++i) {
+        const int r = c.ratios[c.n_ratios - 1 - i];           // the encoder walks the ratios in reverse
+        for (int j = 0; j < c.n_residual_layers; ++j) {
+            int dil = 1;
+            for (int u = 0; u < j; ++u) dil *= c.dilation_base;
+            snprintf(nm, sizeof(nm), "enc.down%d.res%d", i, j);
+            if (res_block(e, nm, x, y, z, pre, B, ch, t_cur, dil, st)) return -1;
+            std::swap(x, pre);
+        }
+        snprintf(nm, sizeof(nm), "enc.down%d.conv.weight", i);
+        if (enc_need(e, nm, &wt)) return -1;
+        snprintf(nm, sizeof(nm), "enc.down%d.conv.bias", i);
+        if (enc_need(e, nm, &bs)) return -1;
+        ConvArgs a = conv_args_strided(e, wt, bs, x, y, ch, 2 * ch, t_cur, 2 * r, r, 1);
+        if (conv_launch(e, a, B, st)) return -1;
+        std::swap(x, y);
+        ch *= 2;
+        t_cur = a.Tout;
+    }
+    if (c.lstm > 0) {
+        if (lstm_stack(e, "enc", x, y, z, pre, B, ch, t_cur, st)) return -1;
+        std::swap(x, y);
+    }
+    if (enc_need(e, "enc.conv_out.weight", &wt) || enc_need(e, "enc.conv_out.bias", &bs)) return -1;
+    if (conv_launch(e, conv_args(e, wt, bs, x, y, ch, c.dimension, t_cur, c.last_kernel_size, 1, 1, nullptr), B, st)) return -1;
+    // ---- residual vector quantisation: y = latent [B, D, T] is consumed as the running residual
+    const int T = t_cur;
+    for (int q = 0; q < c.n_q; ++q) {
+        float *emb, *hsn;
+        snprintf(nm, sizeof(nm), "vq.%d.embed", q);
+        if (enc_need(e, nm, &emb)) return -1;
+        snprintf(nm, sizeof(nm), "vq.%d.__neg_half_sqnorm", q);
+        if (enc_need(e, nm, &hsn)) return -1;
+        // scores[b][code][t] = e_code . resid[b][:, t] - |e_code|^2 / 2   (k = 1 "convolution" with the codebook as weights)
+        if (conv_launch(e, conv_args(e, emb, hsn, y, pre, c.dimension, c.bins, T, 1, 1, 0, nullptr), B, st)) return -1;
+        rvq_pick_kernel<<<dim3((T + 127) / 128, B), 128, 0, st>>>(pre, emb, y, reinterpret_cast<long long*>(codes), c.bins,
+                                                                   c.dimension, T, c.n_q, q);
+        VCB_CUDA_OK(cudaGetLastError());
+        e->launches++;
+    }
+    return 0;
+}
+
 int decode_chunk(enc_engine* e, const int64_t* codes, float* wav, int B, int T, cudaStream_t st) {
     const enc_config& c = e->cfg;
     char nm[128];
@@ -320,32 +480,7 @@ int decode_chunk(enc_engine* e, const int64_t* codes, float* wav, int B, int T, 
     if (conv_launch(e, conv_args(e, wt, bs, x, y, c.dimension, ch, T, c.kernel_size, 1, 0, nullptr), B, st)) return -1;
     std::swap(x, y);                                    // x = conv_in output [B, ch, T]
     if (c.lstm > 0) {
-        const float* layer_in = x;
-        for (int l = 0; l < c.lstm; ++l) {
-            float *wih, *whh, *bsum;
-            snprintf(nm, sizeof(nm), "dec.lstm.weight_ih_l%d", l);
-            if (enc_need(e, nm, &wih)) return -1;
-            snprintf(nm, sizeof(nm), "dec.lstm.weight_hh_l%d", l);
-            if (enc_need(e, nm, &whh)) return -1;
-            snprintf(nm, sizeof(nm), "dec.lstm.__bias_sum_l%d", l);
-            if (enc_need(e, nm, &bsum)) return -1;
-            // pre[B, 4H, T] = W_ih * in + (b_ih + b_hh)   (a k=1 convolution, zero padding irrelevant)
-            ConvArgs a = conv_args(e, wih, bsum, layer_in, pre, ch, 4 * ch, T, 1, 1, 0, nullptr);
-            if (conv_launch(e, a, B, st)) return -1;
-            VCB_CUDA_OK(cudaMemsetAsync(e->h0, 0, static_cast<size_t>(B) * ch * 4, st));
-            VCB_CUDA_OK(cudaMemsetAsync(e->cst, 0, static_cast<size_t>(B) * ch * 4, st));
-            float* seq_out = (l == c.lstm - 1) ? y : z;
-            const float* skip = (l == c.lstm - 1) ? x : nullptr;      // y = LSTM(x) + x   (skip on the stack input)
-            float *hin = e->h0, *hout = e->h1;
-            for (int t = 0; t < T; ++t) {
-                lstm_step_kernel<<<dim3((ch + 7) / 8, (B + 3) / 4), 256, 0, st>>>(pre, whh, hin, hout, e->cst, seq_out,
-                                                                                skip, B, ch, T, t);
-                std::swap(hin, hout);
-            }
-            VCB_CUDA_OK(cudaGetLastError());
-            e->launches += T;
-            layer_in = seq_out;
-        }
+        if (lstm_stack(e, "dec", x, y, z, pre, B, ch, T, st)) return -1;
         std::swap(x, y);                                // x = LSTM output (+ skip)
     }
     int t_cur = T;
@@ -358,7 +493,7 @@ int decode_chunk(enc_engine* e, const int64_t* codes, float* wav, int B, int T, 
         ConvArgs a;
         memset(&a, 0, sizeof(a));
         a.A = wt; a.bias = bs; a.in = x; a.out = y;
-        a.Cin = ch; a.Cout = ch / 2; a.Tin = t_cur; a.Tout = t_cur * r; a.convT = 1; a.r = r; a.elu_in = 1;
+        a.Cin = ch; a.Cout = ch / 2; a.Tin = t_cur; a.Tout = t_cur * r; a.convT = 1; a.r = r; a.elu_in = 1; a.stride = 1;
         const int total = r;                            // kernel 2r - stride r
         const int right = c.causal ? static_cast<int>(ceilf(total * c.trim_right_ratio)) : total / 2;
         a.padL = total - right;                         // samples trimmed on the left
@@ -367,32 +502,10 @@ int decode_chunk(enc_engine* e, const int64_t* codes, float* wav, int B, int T, 
         ch /= 2;
         t_cur *= r;
         for (int j = 0; j < c.n_residual_layers; ++j) {
-            const int hidden = ch / c.compress;
             int dil = 1;
             for (int u = 0; u < j; ++u) dil *= c.dilation_base;
-            float *w1, *b1, *w2, *b2;
-            snprintf(nm, sizeof(nm), "dec.up%d.res%d.conv1.weight", i, j);
-            if (enc_need(e, nm, &w1)) return -1;
-            snprintf(nm, sizeof(nm), "dec.up%d.res%d.conv1.bias", i, j);
-            if (enc_need(e, nm, &b1)) return -1;
-            snprintf(nm, sizeof(nm), "dec.up%d.res%d.conv2.weight", i, j);
-            if (enc_need(e, nm, &w2)) return -1;
-            snprintf(nm, sizeof(nm), "dec.up%d.res%d.conv2.bias", i, j);
-            if (enc_need(e, nm, &b2)) return -1;
-            // h = conv k3(ELU(x)) -> y ; out = shortcut(x) + conv k1(ELU(h))
-            if (conv_launch(e, conv_args(e, w1, b1, x, y, ch, hidden, t_cur, c.residual_kernel_size, dil, 1, nullptr), B, st))
-                return -1;
-            const float* res = x;
-            if (!c.true_skip) {
-                float *ws, *bsc;
-                snprintf(nm, sizeof(nm), "dec.up%d.res%d.shortcut.weight", i, j);
-                if (enc_need(e, nm, &ws)) return -1;
-                snprintf(nm, sizeof(nm), "dec.up%d.res%d.shortcut.bias", i, j);
-                if (enc_need(e, nm, &bsc)) return -1;
-                if (conv_launch(e, conv_args(e, ws, bsc, x, z, ch, ch, t_cur, 1, 1, 0, nullptr), B, st)) return -1;
-                res = z;
-            }
-            if (conv_launch(e, conv_args(e, w2, b2, y, pre, hidden, ch, t_cur, 1, 1, 1, res), B, st)) return -1;
+            snprintf(nm, sizeof(nm), "dec.up%d.res%d", i, j);
+            if (res_block(e, nm, x, y, z, pre, B, ch, t_cur, dil, st)) return -1;
             std::swap(x, pre);
         }
     }
@@ -500,6 +613,31 @@ int enc_finalize(enc_engine* e) {
     }
     flops += t_mult * 2.0 * ch * c.channels * c.last_kernel_size;
     e->flops_per_frame = flops;
+    // encoder side (optional: only when the enc.* weights were loaded)
+    e->has_encoder = e->w.count("enc.conv_in.weight") > 0;
+    if (e->has_encoder) {
+        const int che = c.n_filters << c.n_ratios;
+        for (int l = 0; l < c.lstm; ++l) {
+            float *bi, *bh, *sum;
+            snprintf(nm, sizeof(nm), "enc.lstm.bias_ih_l%d", l);
+            if (enc_need(e, nm, &bi)) return -1;
+            snprintf(nm, sizeof(nm), "enc.lstm.bias_hh_l%d", l);
+            if (enc_need(e, nm, &bh)) return -1;
+            VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sum), 4 * che * sizeof(float)));
+            add_vec_kernel<<<(4 * che + 255) / 256, 256>>>(bi, bh, sum, 4 * che);
+            e->owned.push_back(sum);
+            snprintf(nm, sizeof(nm), "enc.lstm.__bias_sum_l%d", l);
+            e->w[nm] = sum;
+        }
+        for (int q = 0; q < c.n_q; ++q) {
+            float* hsn;
+            VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&hsn), c.bins * sizeof(float)));
+            half_sqnorm_neg_kernel<<<(c.bins + 255) / 256, 256>>>(emb[q], hsn, c.bins, c.dimension);
+            e->owned.push_back(hsn);
+            snprintf(nm, sizeof(nm), "vq.%d.__neg_half_sqnorm", q);
+            e->w[nm] = hsn;
+        }
+    }
     VCB_CUDA_OK(cudaDeviceSynchronize());
     e->finalized = true;
     return 0;
@@ -522,6 +660,34 @@ int enc_decode(enc_engine* e, const int64_t* codes_dev, float* wav_dev, int32_t 
         const int nb = std::min(chunk, B - b0);
         if (decode_chunk(e, codes_dev + static_cast<size_t>(b0) * e->cfg.n_q * T,
                          wav_dev + static_cast<size_t>(b0) * e->cfg.channels * T * e->hop, nb, T, st))
+            return -1;
+    }
+    return 0;
+}
+
+int enc_encode(enc_engine* e, const float* wav_dev, int64_t* codes_dev, int32_t B, int32_t N, void* stream) {
+    if (!e || !e->finalized) {
+        set_error("codec engine not finalized");
+        return -1;
+    }
+    if (!e->has_encoder) {
+        set_error("codec: encoder weights (enc.*) were not loaded");
+        return -1;
+    }
+    if (B < 1 || N < 1) {
+        set_error("codec: empty input (B=%d, N=%d)", B, N);
+        return -1;
+    }
+    VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int T = N;                                           // frames: every strided conv rounds up
+    for (int i = e->cfg.n_ratios - 1; i >= 0; --i) T = (T + e->cfg.ratios[i] - 1) / e->cfg.ratios[i];
+    const int chunk = std::min(B, 16);
+    if (ensure_buffers(e, chunk, (N + e->hop - 1) / e->hop + 1)) return -1;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        if (encode_chunk(e, wav_dev + static_cast<size_t>(b0) * e->cfg.channels * N,
+                         codes_dev + static_cast<size_t>(b0) * e->cfg.n_q * T, nb, N, st))
             return -1;
     }
     return 0;

@@ -1,11 +1,10 @@
-"""Drop-in for the decode side of the reference's ``data/tokenizer.py::AudioTokenizer`` (:101-133).
+"""Drop-in for the reference's ``data/tokenizer.py::AudioTokenizer`` (:101-133).
 
 ``AudioTokenizer(signature=path, device=...)`` mirrors the reference constructor; ``decode(frames)`` takes the
-reference's ``[(codes[1,K,T], None)]`` and returns the waveform ``[1, channels, T*hop]``.  Instead of audiocraft's
-``CompressionSolver.model_from_checkpoint`` + ``EncodecModel.decode`` (:109-110, :133) the weights are handed to
-libvcb200.so, which runs RVQ lookup and the SEANet decoder as sm_100a kernels.  No PyTorch / CPU fallback.
-
-Encoding (``encode``, wav -> codes) and the text tokenizer are out of scope of this build.
+reference's ``[(codes[1,K,T], None)]`` and returns the waveform ``[1, channels, T*hop]``; ``encode(wav[1,C,N])`` returns the
+reference's ``[(codes[1,K,T], None)]`` (:127-129).  Instead of audiocraft's ``CompressionSolver.model_from_checkpoint`` +
+``EncodecModel.decode / encode`` (:109-110, :128, :133) the weights are handed to libvcb200.so, which runs RVQ and the
+SEANet decoder / encoder as sm_100a kernels.  No PyTorch / CPU fallback.  The text tokenizer (espeak) is out of scope.
 """
 import ctypes as C
 from types import SimpleNamespace
@@ -63,6 +62,29 @@ def state_dict_from_audiocraft(sd: dict, cfg) -> dict:
             idx += 1
     idx += 1                                             # ELU
     out["dec.conv_out.weight"], out["dec.conv_out.bias"] = conv(f"decoder.model.{idx}.conv.conv")
+    if "encoder.model.0.conv.conv.weight" in sd or "encoder.model.0.conv.conv.weight_g" in sd:
+        # SEANetEncoder: conv, per ratio (reversed) [ResBlock x n, ELU, strided conv], LSTM, ELU, conv
+        idx = 0
+        out["enc.conv_in.weight"], out["enc.conv_in.bias"] = conv(f"encoder.model.{idx}.conv.conv")
+        idx += 1
+        for i, _ in enumerate(cfg.ratios):
+            for j in range(cfg.n_residual_layers):
+                p = f"encoder.model.{idx}"
+                out[f"enc.down{i}.res{j}.conv1.weight"], out[f"enc.down{i}.res{j}.conv1.bias"] = conv(p + ".block.1.conv.conv")
+                out[f"enc.down{i}.res{j}.conv2.weight"], out[f"enc.down{i}.res{j}.conv2.bias"] = conv(p + ".block.3.conv.conv")
+                if not cfg.true_skip:
+                    out[f"enc.down{i}.res{j}.shortcut.weight"], out[f"enc.down{i}.res{j}.shortcut.bias"] = conv(p + ".shortcut.conv.conv")
+                idx += 1
+            idx += 1                                     # ELU
+            out[f"enc.down{i}.conv.weight"], out[f"enc.down{i}.conv.bias"] = conv(f"encoder.model.{idx}.conv.conv")
+            idx += 1
+        if cfg.lstm:
+            for l in range(cfg.lstm):
+                for part in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                    out[f"enc.lstm.{part}_l{l}"] = sd[f"encoder.model.{idx}.lstm.{part}_l{l}"]
+            idx += 1
+        idx += 1                                         # ELU
+        out["enc.conv_out.weight"], out["enc.conv_out.bias"] = conv(f"encoder.model.{idx}.conv.conv")
     return out
 
 
@@ -139,8 +161,26 @@ class AudioTokenizer:
         except Exception:
             pass
 
+    @torch.no_grad()
+    def encode_codes(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [B,channels,N] fp32 -> codes [B,K,T] int64, T = N down-sampled by every ratio (rounded up)."""
+        assert wav.ndim == 3 and wav.shape[1] == self.channels, wav.shape
+        if "enc.conv_in.weight" not in self._sd:
+            raise _lib.VcbError("this AudioTokenizer was built without encoder weights (enc.*)")
+        eng = self._engine()
+        wav = wav.to(self._device, dtype=torch.float32).contiguous()
+        B, _, N = wav.shape
+        T = N
+        for r in reversed(list(self.config.ratios)):
+            T = (T + int(r) - 1) // int(r)
+        codes = torch.empty(B, self.config.n_q, T, device=self._device, dtype=torch.long)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().enc_encode(eng, wav.data_ptr(), codes.data_ptr(), B, N, torch.cuda.current_stream().cuda_stream))
+        return codes
+
     def encode(self, wav: torch.Tensor):
-        raise NotImplementedError("EnCodec encode (wav -> codes) is outside the decode hot path (SURVEY.md section 8f, f1)")
+        """Reference signature (data/tokenizer.py:127-129): wav [1,C,N] -> [(codes[1,K,T], None)]."""
+        return [(self.encode_codes(wav), None)]
 
     @torch.no_grad()
     def decode_codes(self, codes: torch.Tensor) -> torch.Tensor:
@@ -175,3 +215,27 @@ def save_wav(path, wav: torch.Tensor, sample_rate: int):
         f.setsampwidth(2)
         f.setframerate(int(sample_rate))
         f.writeframes(pcm.tobytes())
+
+
+def tokenize_audio(tokenizer: AudioTokenizer, audio_path: str, offset=-1, num_frames=-1):
+    """The reference's helper (data/tokenizer.py:137-149) for 16-bit PCM WAV files, without the torchaudio dependency:
+    load (optionally a window of `num_frames` samples from `offset`), mix to the codec's channel count, encode.
+    A file at another sample rate is rejected (the reference resamples with torchaudio; do that before calling)."""
+    import wave
+    import numpy as np
+    with wave.open(str(audio_path), "rb") as f:
+        sr, ch, n, width = f.getframerate(), f.getnchannels(), f.getnframes(), f.getsampwidth()
+        if width != 2:
+            raise ValueError("tokenize_audio: 16-bit PCM WAV expected")
+        if offset != -1 and num_frames != -1:
+            f.setpos(min(int(offset), n))
+            n = min(int(num_frames), n - f.tell())
+        pcm = np.frombuffer(f.readframes(n), dtype="<i2").reshape(-1, ch).T.astype(np.float32) / 32768.0
+    if sr != tokenizer.sample_rate:
+        raise ValueError(f"tokenize_audio: file is {sr} Hz, the codec runs at {tokenizer.sample_rate} Hz (resample first)")
+    wav = torch.from_numpy(np.ascontiguousarray(pcm))
+    if wav.shape[0] != tokenizer.channels:                    # convert_audio (:77-99): down-mix / broadcast
+        wav = wav.mean(dim=0, keepdim=True).expand(tokenizer.channels, -1) if tokenizer.channels == 1 or wav.shape[0] > 1 \
+            else wav.expand(tokenizer.channels, -1)
+    with torch.no_grad():
+        return tokenizer.encode(wav.unsqueeze(0))
