@@ -115,7 +115,8 @@ struct vcb_engine {
     int opt_simt = 0, opt_pdl = 0, opt_profile = 0, opt_gemm_maxctas = 0, opt_gemm_stages = 0, opt_prefetch = 0, opt_att_balance = 1;
     // wide prefill (gemm_rows.cu): up to wide_rows prompt rows per pass through the layers, own activation planes;
     // opt_prefill_wide = minimum number of prompt rows that takes this path (0: never; VCB_PREFILL_WIDE)
-    int opt_prefill_wide = 256, wide_rows = 0;
+    int opt_prefill_wide = 1, wide_rows = 0;      // 1: every prompt takes the rows-as-M path, so a row's K/V bits do not
+                                                  // depend on how many other prompts were prefilled with it
     int opt_att_group = 0;            // EXPERIMENTAL: rows per work item of the wide prefill attention (0 / 4; prefill_attn.cuh)
     float *wx = nullptr, *wq = nullptr, *w_att_ws = nullptr;
     int* w_att_cnt = nullptr;
@@ -1529,20 +1530,21 @@ int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float*
     return sample_rows(e, n, e->x_rows, nullptr, exp_noise_dev, sp, fold, st);
 }
 
+// a failed synchronisation: if the persistent kernel's watchdog fired, say where (the record is in mapped host memory)
+static int sync_or_report(vcb_engine* e, cudaError_t se, const char* what) {
+    if (se == cudaSuccess) return 0;
+    if (e->mega_dbg_h && e->mega_dbg_h[0])
+        set_error("%s: decode step kernel: bounded wait expired (role %u, phase %u, cta %u, info 0x%x): %s", what, e->mega_dbg_h[1],
+                  e->mega_dbg_h[2], e->mega_dbg_h[3], e->mega_dbg_h[4], cudaGetErrorString(se));
+    else
+        set_error("%s: %s", what, cudaGetErrorString(se));
+    return -1;
+}
+
 int vcb_poll(vcb_engine* e, const int32_t* slots, int32_t n, vcb_status* out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     VCB_CUDA_OK(cudaSetDevice(e->cfg.device));
-    {
-        const cudaError_t se = cudaStreamSynchronize(st);
-        if (se != cudaSuccess) {
-            if (e->mega_dbg_h && e->mega_dbg_h[0])
-                set_error("decode step kernel: bounded wait expired (role %u, phase %u, cta %u, info 0x%x): %s", e->mega_dbg_h[1],
-                          e->mega_dbg_h[2], e->mega_dbg_h[3], e->mega_dbg_h[4], cudaGetErrorString(se));
-            else
-                set_error("vcb_poll: %s", cudaGetErrorString(se));
-            return -1;
-        }
-    }
+    if (sync_or_report(e, cudaStreamSynchronize(st), "vcb_poll")) return -1;
     if (e->chain_epoch != 0) {
         unsigned int flag = 0;
         VCB_CUDA_OK(cudaMemcpy(&flag, e->chain_ctr + 1, 4, cudaMemcpyDeviceToHost));
@@ -1605,6 +1607,7 @@ int vcb_release(vcb_engine* e, int32_t slot, int32_t n_copies) {
 }
 
 int vcb_debug_logits(vcb_engine* e, float* out_dev, int32_t n_rows) {
+    if (sync_or_report(e, cudaDeviceSynchronize(), "vcb_debug_logits")) return -1;
     VCB_CUDA_OK(cudaMemcpy(out_dev, e->dbg_logits, static_cast<size_t>(n_rows) * e->m.V * sizeof(float),
                            cudaMemcpyDeviceToDevice));
     return 0;
@@ -1813,7 +1816,7 @@ int vcb_debug_mega_timeline(vcb_engine* e, uint64_t* out_host, int32_t max_recor
         VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->mega_tl), n * 8));
         VCB_CUDA_OK(cudaMemset(e->mega_tl, 0, n * 8));
     }
-    VCB_CUDA_OK(cudaDeviceSynchronize());
+    if (sync_or_report(e, cudaDeviceSynchronize(), "vcb_debug_mega_timeline")) return -1;
     if (out_host && max_records > 0)
         VCB_CUDA_OK(cudaMemcpy(out_host, e->mega_tl, std::min<size_t>(n, max_records) * 8, cudaMemcpyDeviceToHost));
     if (n_phases) *n_phases = e->mega_nph;

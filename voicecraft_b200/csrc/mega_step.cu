@@ -116,6 +116,18 @@ __device__ __forceinline__ void mg_wait_flag(const unsigned int* flag, unsigned 
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void mg_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// wait until the ring producer has issued ring item `item` (s_prod = number of items issued so far)
+__device__ __forceinline__ void mg_wait_issued(volatile uint32_t* s_prod, uint32_t item, unsigned int* dbg, unsigned int phase) {
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0; static_cast<int32_t>(*s_prod - item) <= 0; ++spins) {
+        __nanosleep(20);
+        if ((spins & 0xfffu) == 0xfffu) {
+            const unsigned long long t = mg_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) mg_die(dbg, 8, phase, 0x300u);
+        }
+    }
+}
 
 // Work split of T units over the first Ge = min(G, T) CTAs (every one of them gets >= 1 unit, the others none, so the
 // CTAs that share a tile / an attention item are always consecutive): range of CTA c, and the CTA that owns unit u.
@@ -757,6 +769,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             ks[j] = (itu + j) % MG_NS;
                             vs[j] = (itu + NSL + j) % MG_NS;
                         }
+                        // The 8 warps run up to 16 ring items apart, more than the ring holds: a warp may ask for use n of a
+                        // slot while use n-1 (another warp's page) has not even landed, and a 1-bit phase parity cannot tell
+                        // n from n-2.  So first wait until the producer has ISSUED the item (it only does so after use n-1
+                        // was consumed and released), then wait for the data.
+                        mg_wait_issued(s_prod, itu + NSL - 1, A.dbg, p);
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((itu + j) / MG_NS) & 1, A.dbg, 6, p);
                         // scores: 2 keys per iteration (16 lanes x 8 dims each), xor-shuffle reduce
@@ -789,6 +806,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                         pww[lane + 32] = e1;
                         const float l_pg = warp_sum(e0 + e1);
                         __syncwarp();
+                        mg_wait_issued(s_prod, itu + 2 * NSL - 1, A.dbg, p);
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((itu + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
                         float acc[DPT];
