@@ -41,7 +41,7 @@ static constexpr int MG_BSLOT = 8192;          // 64 rows (32 hi + 32 lo) x 64 k
 static constexpr int MG_NACC = 4;              // TMEM accumulator stages
 static constexpr int MG_HD = 128;
 static constexpr int MG_PAGE = 64;
-static constexpr int MG_NPB = 32;              // attention: units per merge batch
+static constexpr int MG_CHUNK = 4;             // attention: pages per work item (a chunk of one (row, head))
 static constexpr int MG_PSTR = 132;            // floats per page partial: acc[128], m, l, pad
 
 struct MegaSmem {
@@ -51,11 +51,8 @@ struct MegaSmem {
     static constexpr int MISC = BAR + NBAR * 8;                    // tmem slot, flags, producer progress, page-count table
     static constexpr int TOTAL = MISC + 32 + 34 * 4 + 64;
     // attention scratch, aliased onto the B ring (idle during an attention phase)
-    static constexpr int A_PART = 0;                                // page partials [MG_NPB + 1][MG_PSTR] floats (+1: carry)
-    static constexpr int A_SCW = A_PART + (MG_NPB + 1) * MG_PSTR * 4;   // per-warp scores [8][64]
-    static constexpr int A_PWW = A_SCW + 8 * MG_PAGE * 4;           // per-warp probabilities [8][64]
-    static constexpr int A_ITEM = A_PWW + 8 * MG_PAGE * 4;          // merged item: o[128], m, l
-    static constexpr int A_END = A_ITEM + MG_PSTR * 4;
+    static constexpr int A_STATE = 0;                               // per-warp chunk states [8][MG_PSTR] floats
+    static constexpr int A_END = A_STATE + 8 * MG_PSTR * 4;
 };
 static_assert(MegaSmem::A_END <= 3 * MG_BSLOT, "attention scratch must fit three B slots (nb >= 3)");
 static_assert(MegaSmem::TOTAL <= 232448, "shared memory budget of one CTA per SM");
@@ -140,6 +137,23 @@ __device__ __forceinline__ void mg_range(long long T, int c, int Ge, int& b0, in
     b0 = static_cast<int>(T * c / Ge);
     b1 = static_cast<int>(T * (c + 1) / Ge);
 }
+// attention unit u -> (row, head, page) and the row's page count; units are ordered (row, head, page)
+__device__ __forceinline__ void mg_locate(const int* s_cum, int H, int u, int& r, int& h, int& pg, int& npg) {
+    r = 0;
+    while (r < 31 && static_cast<long long>(H) * s_cum[r + 1] <= u) ++r;
+    npg = s_cum[r + 1] - s_cum[r];
+    const int rem = u - H * s_cum[r];
+    h = npg ? rem / npg : 0;
+    pg = npg ? rem - h * npg : 0;
+}
+// first chunk boundary at or after unit u (chunks = MG_CHUNK pages of one (row, head), the last one shorter)
+__device__ __forceinline__ int mg_chunk_align(const int* s_cum, int H, int u, long long U) {
+    if (u >= U) return static_cast<int>(U);
+    int r, h, pg, npg;
+    mg_locate(s_cum, H, u, r, h, pg, npg);
+    const int m = pg % MG_CHUNK;
+    return m == 0 ? u : u + min(MG_CHUNK - m, npg - pg);
+}
 // debug timeline: every CTA records %globaltimer at fixed (cta, phase, event) slots
 __device__ __forceinline__ void mg_tl(const MegaArgs& A, int p, int ev) {
     if (A.tl != nullptr) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 8 + ev] = mg_now();
@@ -163,11 +177,23 @@ template <int BPAD>
 __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPhase& P, int p, int tile, int c_first, int ncontrib,
                                                  long long T, int G, int wq, int lane) {
     constexpr int RPW = BPAD / 8;
-    const GemmEpilogue& ep = P.ep;
+    // The descriptor is copied into registers / local memory ONCE: read through a reference into global memory, every field
+    // would be re-loaded after each of the epilogue's global stores (possible aliasing), and the per-row position / page
+    // look-ups would become chains of dependent L2 round trips between the stores (measured: ~9 us per tile).
+    const GemmEpilogue ep = P.ep;
     const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
     const int m0 = tl * 128 + 4 * lane;                       // first of my 4 features (group-local)
     const int Nout = P.Nout;
     const int row_base = wq * RPW;
+    const int col_grp = g * P.col_grp_stride;
+    int rpos[RPW], rpage[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int row = row_base + rr;
+        const bool live = ep.mode == EPI_QKV && row < A.nvalid;
+        rpos[rr] = live ? ep.row_pos[row] : -1;
+        rpage[rr] = live ? ep.row_page[row] : 0;
+    }
     // ---- operands that do not depend on the reduction ------------------------------------------------------------------
     const float* bias_ptr = P.grp_bias ? P.grp_bias[g] : ep.bias;
     float bias[4], cv[4], gn[4];
@@ -249,14 +275,14 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
         if (row_ok) {
             switch (ep.mode) {
                 case EPI_QKV: {
-                    const int pos = ep.row_pos[row];
+                    const int pos = rpos[rr];
                     if (pos < 0 || m0 >= Nout) break;
                     const int part = m0 / ep.d, cc = m0 - part * ep.d;
                     if (part == 0) {
                         __stcg(reinterpret_cast<float4*>(ep.qbuf + static_cast<size_t>(row) * ep.d + cc), make_float4(a[0], a[1], a[2], a[3]));
                         break;
                     }
-                    const int page = ep.row_page[row];
+                    const int page = rpage[rr];
                     const int h = cc / ep.hd, e = cc - h * ep.hd;
                     const size_t off = ((static_cast<size_t>(page) * ep.H + h) * ep.page_size + pos % ep.page_size) * ep.hd + e;
                     void* pool = (part == 1) ? ep.kpool : ep.vpool;
@@ -297,7 +323,7 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
                     break;
                 }
                 default: {
-                    float* o = ep.out + static_cast<size_t>(row) * ep.ld_out + ep.col_off + g * P.col_grp_stride + m0;
+                    float* o = ep.out + static_cast<size_t>(row) * ep.ld_out + ep.col_off + col_grp + m0;
                     if (m0 + 3 < Nout) {
                         __stcg(reinterpret_cast<float4*>(o), make_float4(a[0], a[1], a[2], a[3]));
                     } else {
@@ -427,6 +453,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
     int u0, u1;
     const int Ue = mg_eff(U, G);
     mg_range(U, cta, Ue, u0, u1);
+    u0 = mg_chunk_align(s_cum, A.H, u0, U);            // a CTA owns the chunks that START in its share of the units
+    u1 = mg_chunk_align(s_cum, A.H, u1, U);
     const int att_items = (u1 - u0) * 2 * NSL;                        // ring items of one attention phase (this CTA)
 
     if (warp == 0) {
@@ -521,6 +549,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     tc_fence_after();
                     if (lane >= 1 && lane < 8) mbar_arrive(&empty[s]);      // 7 of the slot's 8 release arrivals
                     if (lane == 0) {
+                        if (first && blk == b0) mg_tl(A, p, 5);
                         const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(ring + s * MG_SLOT));
                         const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(bring + bs * MG_BSLOT));
 #pragma unroll
@@ -528,6 +557,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                         umma_commit(&empty[s]);                             // the 8th: when these MMAs have read the slot
                         umma_commit(&bempty[bs]);
                         if (blk == seg_end - 1) umma_commit(&accfull[stage]);
+                        if (blk == b1 - 1) mg_tl(A, p, 6);
                     }
                     __syncwarp();
                 }
@@ -557,6 +587,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     mbar_arrive_expect_tx(&bfull[bs], B_BYTES);
                     tma_load_2d(bring + bs * MG_BSLOT, &A.tmB[P.b_map], &bfull[bs], P.b_col_off + g * P.b_grp_stride + kbi * 64, 0);
                 }
+                mg_tl(A, p, 4);
             }
         }
     } else if (warp == 3) {
@@ -704,82 +735,82 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     if (wtid == 0) mg_tl(A, p, 3);
                 }
             } else {
-                // ===== attention: units [u0, u1) ========================================================================
-                // One WARP per (row, head, page) unit: scores, softmax and PV of a 64-key page need no other warp, so the 8
-                // worker warps run 8 pages concurrently and never meet at a block barrier inside a page.  A page yields an
-                // independent partial (acc[128], m, l); per batch of MG_NPB units the partials of each (row, head) item are merged
-                // in page order (one extra "carry" slot holds an item that continues into the next batch), then the item goes
-                // out directly (whole item in this CTA) or through the cross-CTA merge.
+                // ===== attention: units [u0, u1), cut at chunk boundaries ======================================================
+                // Work item = CHUNK of up to MG_CHUNK consecutive pages of one (row, head); the chunk grid depends only on the
+                // row's own context length.  The 8 worker warps share every page: warp w scores keys [8w, 8w+8) of the page,
+                // keeps its own online-softmax state (m, l, acc) over the chunk's pages and multiplies its 8 probabilities
+                // into V -- no block barrier per page, so a K/V slab leaves the ring ~0.3 us after it lands (the ring's
+                // residence time, not the math, bounds the HBM stream).  Per chunk: the 8 warp states fold in warp order,
+                // a one-chunk item goes out directly, otherwise the chunk state is published and the last chunk to arrive
+                // folds all chunk states in chunk order.  Every result is a fixed-order fold that depends only on the row's
+                // own context -- a row's tokens do not depend on what else is in the batch.
                 constexpr int LPT = MG_HD / 8, DPT = MG_HD / 32;
-                float* part_sm = reinterpret_cast<float*>(bring + L::A_PART);        // [MG_NPB + 1][MG_PSTR]
-                float* scw = reinterpret_cast<float*>(bring + L::A_SCW) + wq * MG_PAGE;
-                float* pww = reinterpret_cast<float*>(bring + L::A_PWW) + wq * MG_PAGE;
-                float* item_sm = reinterpret_cast<float*>(bring + L::A_ITEM);         // merged item: o[128], m, l
+                float* st_sm = reinterpret_cast<float*>(bring + L::A_STATE);         // [8 warps][MG_PSTR]
                 if (P.dep_target > 0) {
                     if (lane == 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 5, p);
                     __syncwarp();
                 }
                 if (wtid == 0) mg_tl(A, p, 4);
-                const int sub = lane % LPT;
+                const int sub = lane % LPT, half = lane / LPT;
                 const uint32_t it0 = it;
-                // unit -> (row, head, page)
-                auto locate = [&](int u, int& r, int& h, int& pg, int& npg) {
-                    r = 0;
-                    while (r < 31 && static_cast<long long>(A.H) * s_cum[r + 1] <= u) ++r;
-                    npg = s_cum[r + 1] - s_cum[r];
-                    const int rem = u - A.H * s_cum[r];
-                    h = rem / npg;
-                    pg = rem - h * npg;
+                // operands of a chunk that come from this step's QKV epilogue: q, and the current position's k / v if the chunk
+                // holds it.  Loaded one chunk ahead (L2 round trip off the critical path).
+                auto fetch = [&](int u, float (&q8)[8], float (&k8)[8], float (&v4)[DPT]) {
+                    int r, h, pg, npg;
+                    mg_locate(s_cum, A.H, u, r, h, pg, npg);
+                    const size_t base = (static_cast<size_t>(r) * A.H + h) * MG_HD;
+                    const float4* qp = reinterpret_cast<const float4*>(A.qbuf + base + sub * 8);
+                    const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
+                    q8[0] = q0.x; q8[1] = q0.y; q8[2] = q0.z; q8[3] = q0.w;
+                    q8[4] = q1.x; q8[5] = q1.y; q8[6] = q1.z; q8[7] = q1.w;
+                    if (pg + MG_CHUNK >= npg) {                                      // the chunk holds the row's last page
+                        const float4* kp = reinterpret_cast<const float4*>(A.knew + base + sub * 8);
+                        const float4 k0 = __ldcg(kp), k1 = __ldcg(kp + 1);
+                        k8[0] = k0.x; k8[1] = k0.y; k8[2] = k0.z; k8[3] = k0.w;
+                        k8[4] = k1.x; k8[5] = k1.y; k8[6] = k1.z; k8[7] = k1.w;
+                        const float4 v0 = __ldcg(reinterpret_cast<const float4*>(A.vnew + base + lane * DPT));
+                        v4[0] = v0.x; v4[1] = v0.y; v4[2] = v0.z; v4[3] = v0.w;
+                    }
                 };
-                int carry_rh = -1;                                                  // item continued from the previous batch
-                for (int ub = u0; ub < u1; ub += MG_NPB) {
-                    const int ue = min(u1, ub + MG_NPB);
-                    // ---- (1) pages: warp wq takes units ub + wq, ub + wq + 8, ... -------------------------------------------------
-                    for (int u = ub + wq; u < ue; u += 8) {
-                        int r, h, pgi, npg;
-                        locate(u, r, h, pgi, npg);
-                        const int pos = A.row_pos[r];
-                        const int rh = r * A.H + h;
-                        const uint32_t itu = it0 + static_cast<uint32_t>(u - u0) * 2 * NSL;
-                        float qv[8];
-                        {
-                            const float4* qp = reinterpret_cast<const float4*>(A.qbuf + static_cast<size_t>(rh) * MG_HD + sub * 8);
-                            const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
-                            qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w;
-                            qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-                        }
-                        const bool self_page = pgi == npg - 1;                      // holds the current position
-                        const int self_t = self_page ? pos - pgi * MG_PAGE : -1;
-                        float kself[8], vself[DPT];
+                float qn[8], kn[8], vn[DPT];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) kself[i] = 0.f;
+                for (int i = 0; i < 8; ++i) qn[i] = kn[i] = 0.f;
 #pragma unroll
-                        for (int i = 0; i < DPT; ++i) vself[i] = 0.f;
-                        if (self_page) {
-                            const float4* kp = reinterpret_cast<const float4*>(A.knew + static_cast<size_t>(rh) * MG_HD + sub * 8);
-                            const float4 k0 = __ldcg(kp), k1 = __ldcg(kp + 1);
-                            kself[0] = k0.x; kself[1] = k0.y; kself[2] = k0.z; kself[3] = k0.w;
-                            kself[4] = k1.x; kself[5] = k1.y; kself[6] = k1.z; kself[7] = k1.w;
-                            const float4 v0 = __ldcg(reinterpret_cast<const float4*>(A.vnew + static_cast<size_t>(rh) * MG_HD + lane * DPT));
-                            vself[0] = v0.x; vself[1] = v0.y; vself[2] = v0.z; vself[3] = v0.w;
-                        }
+                for (int i = 0; i < DPT; ++i) vn[i] = 0.f;
+                if (u0 < u1) fetch(u0, qn, kn, vn);
+                int u = u0;
+                while (u < u1) {
+                    int r, h, pg, npg;
+                    mg_locate(s_cum, A.H, u, r, h, pg, npg);
+                    const int pe = min(npg, pg + MG_CHUNK);
+                    const int pos = A.row_pos[r];
+                    const int rh = r * A.H + h;
+                    float qv[8], kself[8], vself[DPT];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { qv[i] = qn[i]; kself[i] = kn[i]; }
+#pragma unroll
+                    for (int i = 0; i < DPT; ++i) vself[i] = vn[i];
+                    if (u + (pe - pg) < u1) fetch(u + (pe - pg), qn, kn, vn);       // next chunk's operands
+                    float m_run = -INFINITY, l_run = 0.f;
+                    float acc[DPT];
+#pragma unroll
+                    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+                    for (int pgi = pg; pgi < pe; ++pgi) {
+                        const uint32_t itu = it0 + static_cast<uint32_t>(u - u0 + (pgi - pg)) * 2 * NSL;
                         uint32_t ks[NSL], vs[NSL];
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) {
                             ks[j] = (itu + j) % MG_NS;
                             vs[j] = (itu + NSL + j) % MG_NS;
                         }
-                        // The 8 warps run up to 16 ring items apart, more than the ring holds: a warp may ask for use n of a
-                        // slot while use n-1 (another warp's page) has not even landed, and a 1-bit phase parity cannot tell
-                        // n from n-2.  So first wait until the producer has ISSUED the item (it only does so after use n-1
-                        // was consumed and released), then wait for the data.
-                        mg_wait_issued(s_prod, itu + NSL - 1, A.dbg, p);
+                        const int self_t = (pgi == npg - 1) ? pos - pgi * MG_PAGE : -1;
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((itu + j) / MG_NS) & 1, A.dbg, 6, p);
-                        // scores: 2 keys per iteration (16 lanes x 8 dims each), xor-shuffle reduce
-#pragma unroll 4
-                        for (int kk = 0; kk < MG_PAGE / 2; ++kk) {
-                            const int t = 2 * kk + lane / LPT;
+                        // ---- scores of my 8 keys: 2 per iteration (one per half-warp), xor-reduce inside the half-warp
+                        float sc[4];
+#pragma unroll
+                        for (int itq = 0; itq < 4; ++itq) {
+                            const int t = wq * 8 + itq * 2 + half;
                             float kvv[8];
                             const KVT* Kp = reinterpret_cast<const KVT*>(ring + ks[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + sub * 8;
                             mg_load_kv<KVT, 8>(Kp, kvv);
@@ -792,146 +823,132 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             for (int i = 0; i < 8; ++i) dsum = fmaf(qv[i], kvv[i], dsum);
 #pragma unroll
                             for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-                            if (sub == 0) scw[t] = (pgi * MG_PAGE + t <= pos) ? dsum * A.scale : -INFINITY;
+                            sc[itq] = (pgi * MG_PAGE + t <= pos) ? dsum * A.scale : -INFINITY;
                         }
                         __syncwarp();
-                        if (lane < 8) {
+                        if (lane == 0) {
 #pragma unroll
-                            for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[ks[j]]);       // 8 arrivals release the slot
+                            for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[ks[j]]);       // one of the 8 warps' arrivals
                         }
-                        const float s0 = scw[lane], s1 = scw[lane + 32];
-                        const float m_pg = warp_max(fmaxf(s0, s1));                 // finite: key 0 of page 0 / the self key is live
-                        const float e0 = expf(s0 - m_pg), e1 = expf(s1 - m_pg);
-                        pww[lane] = e0;
-                        pww[lane + 32] = e1;
-                        const float l_pg = warp_sum(e0 + e1);
-                        __syncwarp();
-                        mg_wait_issued(s_prod, itu + 2 * NSL - 1, A.dbg, p);
+                        // ---- online softmax over my key slice
+                        float pm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+                        pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 16));
+                        const float m_new = fmaxf(m_run, pm);
+                        float pr[4], corr = 1.f, psum = 0.f;
+                        if (m_new == -INFINITY) {                                   // every key of my slice masked so far
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) pr[i] = 0.f;
+                        } else {
+                            corr = expf(m_run - m_new);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                pr[i] = expf(sc[i] - m_new);
+                                psum += pr[i];
+                            }
+                        }
+                        psum += __shfl_xor_sync(0xffffffffu, psum, 16);
+                        l_run = l_run * corr + psum;
+                        m_run = m_new;
+#pragma unroll
+                        for (int i = 0; i < DPT; ++i) acc[i] *= corr;
+                        // ---- PV over my 8 keys
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((itu + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
-                        float acc[DPT];
 #pragma unroll
-                        for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
-#pragma unroll 8
-                        for (int t = 0; t < MG_PAGE; ++t) {
-                            const float pt_ = pww[t];
-                            float vv[DPT];
-                            const KVT* Vp = reinterpret_cast<const KVT*>(ring + vs[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + lane * DPT;
-                            mg_load_kv<KVT, DPT>(Vp, vv);
-                            if (t == self_t) {
+                        for (int itq = 0; itq < 4; ++itq) {
+                            const float po = __shfl_xor_sync(0xffffffffu, pr[itq], 16);
+                            const float p0 = half == 0 ? pr[itq] : po, p1 = half == 0 ? po : pr[itq];
 #pragma unroll
-                                for (int i = 0; i < DPT; ++i) vv[i] = vself[i];
+                            for (int gk = 0; gk < 2; ++gk) {
+                                const int t = wq * 8 + itq * 2 + gk;
+                                float vv[DPT];
+                                const KVT* Vp = reinterpret_cast<const KVT*>(ring + vs[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + lane * DPT;
+                                mg_load_kv<KVT, DPT>(Vp, vv);
+                                if (t == self_t) {
+#pragma unroll
+                                    for (int i = 0; i < DPT; ++i) vv[i] = vself[i];
+                                }
+                                const float pk = gk == 0 ? p0 : p1;
+#pragma unroll
+                                for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pk, vv[i], acc[i]);
                             }
-#pragma unroll
-                            for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pt_, vv[i], acc[i]);
                         }
                         __syncwarp();
-                        if (lane < 8) {
+                        if (lane == 0) {
 #pragma unroll
                             for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[vs[j]]);
                         }
-                        float* ps = part_sm + (u - ub) * MG_PSTR;
+                    }
+                    // ---- chunk done: fold the 8 warp states in warp order ----------------------------------------------------------
+                    {
+                        float* ps = st_sm + wq * MG_PSTR;
                         *reinterpret_cast<float4*>(ps + lane * DPT) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                         if (lane == 0) {
-                            ps[MG_HD] = m_pg;
-                            ps[MG_HD + 1] = l_pg;
+                            ps[MG_HD] = m_run;
+                            ps[MG_HD + 1] = l_run;
                         }
                     }
                     mg_bar_workers();
-                    // ---- (2) fold the batch's page partials per item -------------------------------------------------------------
-                    // Canonical result: an item's output is the left fold of its page partials in page order,
-                    //   (O, M, L) <- (O e^{M-M'} + a_p e^{m_p-M'}, M' = max(M, m_p), L e^{M-M'} + l_p e^{m_p-M'}),
-                    // no matter which warp or CTA computed a page -- so a row's tokens do not depend on what else is in the batch.
-                    // Items inside this CTA's range fold in shared memory (the carry slot continues across batches); items shared
-                    // with neighbouring CTAs publish their page partials, and the last CTA to arrive folds all pages.
-                    int u = ub;
-                    while (u < ue) {
-                        int r, h, pg, npg;
-                        locate(u, r, h, pg, npg);
-                        const int rh = r * A.H + h;
-                        const int gb = min(ue, u + (npg - pg));                     // units [u, gb) belong to this item
-                        const int pb = pg + (gb - u);                               // one past the last page of this piece
-                        const long long ui0 = static_cast<long long>(A.H) * s_cum[r] + static_cast<long long>(h) * npg;
-                        const bool spans = ui0 < u0 || ui0 + npg > u1;              // item shared with other CTAs
-                        const bool more = (gb == ue) && (ue < u1) && (pb < npg);    // continues in this CTA's next batch
-                        const size_t ocol = static_cast<size_t>(h) * MG_HD;
-                        if (!spans) {
+                    const int n_chunks = (npg + MG_CHUNK - 1) / MG_CHUNK, cidx = pg / MG_CHUNK;
+                    const size_t ocol = static_cast<size_t>(h) * MG_HD;
+                    float* wsi = A.att_ws + static_cast<size_t>(rh) * A.max_pages * MG_PSTR;
+                    if (wtid < MG_HD) {
+                        float M = -INFINITY, Ls = 0.f, O = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            const float* ps = st_sm + w * MG_PSTR;
+                            const float mp = ps[MG_HD];
+                            if (mp == -INFINITY) continue;                          // that warp's key slice was fully masked
+                            const float Mn = fmaxf(M, mp);
+                            const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
+                            Ls = Ls * c1 + ps[MG_HD + 1] * c2;
+                            O = O * c1 + ps[wtid] * c2;
+                            M = Mn;
+                        }
+                        if (n_chunks == 1) {
+                            const float o = O / Ls;
+                            __nv_bfloat16 hi, lo;
+                            split_bf16(o, hi, lo);
+                            A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                            A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                        } else {
+                            __stcg(wsi + static_cast<size_t>(cidx) * MG_PSTR + wtid, O);
+                            if (wtid == 0) {
+                                __stcg(wsi + static_cast<size_t>(cidx) * MG_PSTR + MG_HD, M);
+                                __stcg(wsi + static_cast<size_t>(cidx) * MG_PSTR + MG_HD + 1, Ls);
+                            }
+                        }
+                    }
+                    if (n_chunks > 1) {
+                        mg_bar_workers();
+                        if (wtid == 0) {
+                            __threadfence();
+                            *s_flag = (atomicAdd(A.att_cnt + rh, 1) == n_chunks - 1);
+                            __threadfence();
+                        }
+                        mg_bar_workers();
+                        if (*s_flag) {
                             if (wtid < MG_HD) {
-                                const bool cont_in = carry_rh == rh;
-                                float M = cont_in ? part_sm[MG_NPB * MG_PSTR + MG_HD] : -INFINITY;
-                                float Ls = cont_in ? part_sm[MG_NPB * MG_PSTR + MG_HD + 1] : 0.f;
-                                float O = cont_in ? part_sm[MG_NPB * MG_PSTR + wtid] : 0.f;
-                                for (int j = u; j < gb; ++j) {
-                                    const float* ps = part_sm + (j - ub) * MG_PSTR;
-                                    const float mp = ps[MG_HD], Mn = fmaxf(M, mp);
+                                float M = -INFINITY, Ls = 0.f, O = 0.f;
+                                for (int j = 0; j < n_chunks; ++j) {
+                                    const float* ps = wsi + static_cast<size_t>(j) * MG_PSTR;
+                                    const float mp = __ldcg(ps + MG_HD), Mn = fmaxf(M, mp);
                                     const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
-                                    Ls = Ls * c1 + ps[MG_HD + 1] * c2;
-                                    O = O * c1 + ps[wtid] * c2;
+                                    Ls = Ls * c1 + __ldcg(ps + MG_HD + 1) * c2;
+                                    O = O * c1 + __ldcg(ps + wtid) * c2;
                                     M = Mn;
                                 }
-                                if (more) {
-                                    item_sm[wtid] = O;
-                                    if (wtid == 0) {
-                                        item_sm[MG_HD] = M;
-                                        item_sm[MG_HD + 1] = Ls;
-                                    }
-                                } else {
-                                    const float o = O / Ls;
-                                    __nv_bfloat16 hi, lo;
-                                    split_bf16(o, hi, lo);
-                                    A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                                    A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
-                                }
+                                const float o = O / Ls;
+                                __nv_bfloat16 hi, lo;
+                                split_bf16(o, hi, lo);
+                                A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                                A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
                             }
-                            mg_bar_workers();
-                            if (more) {
-                                if (wtid < MG_HD + 2) part_sm[MG_NPB * MG_PSTR + wtid] = item_sm[wtid];
-                                carry_rh = rh;
-                            } else {
-                                carry_rh = -1;
-                            }
-                        } else {
-                            float* wsi = A.att_ws + static_cast<size_t>(rh) * A.max_pages * MG_PSTR;
-                            for (int i = wtid; i < (gb - u) * (MG_HD + 2); i += MG_WORKERS) {
-                                const int j = i / (MG_HD + 2), e = i - j * (MG_HD + 2);
-                                __stcg(wsi + static_cast<size_t>(pg + j) * MG_PSTR + e, part_sm[(u - ub + j) * MG_PSTR + e]);
-                            }
-                            if (!more) {
-                                // my last piece of this item: publish, count; the last CTA folds pages 0 .. npg-1
-                                const int c_first = mg_owner(ui0, U, Ue), c_last = mg_owner(ui0 + npg - 1, U, Ue);
-                                const int nch = c_last - c_first + 1;
-                                mg_bar_workers();
-                                if (wtid == 0) {
-                                    __threadfence();
-                                    *s_flag = (atomicAdd(A.att_cnt + rh, 1) == nch - 1);
-                                    __threadfence();
-                                }
-                                mg_bar_workers();
-                                if (*s_flag) {
-                                    if (wtid < MG_HD) {
-                                        float M = -INFINITY, Ls = 0.f, O = 0.f;
-                                        for (int j = 0; j < npg; ++j) {
-                                            const float* ps = wsi + static_cast<size_t>(j) * MG_PSTR;
-                                            const float mp = __ldcg(ps + MG_HD), Mn = fmaxf(M, mp);
-                                            const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
-                                            Ls = Ls * c1 + __ldcg(ps + MG_HD + 1) * c2;
-                                            O = O * c1 + __ldcg(ps + wtid) * c2;
-                                            M = Mn;
-                                        }
-                                        const float o = O / Ls;
-                                        __nv_bfloat16 hi, lo;
-                                        split_bf16(o, hi, lo);
-                                        A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                                        A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
-                                    }
-                                    if (wtid == 0) A.att_cnt[rh] = 0;
-                                }
-                            }
-                            carry_rh = -1;
+                            if (wtid == 0) A.att_cnt[rh] = 0;
                         }
-                        mg_bar_workers();                                           // partial slots / item_sm / s_flag are reused
-                        u = gb;
                     }
+                    mg_bar_workers();                                               // warp states / s_flag are reused
+                    u += pe - pg;
                 }
                 it = it0 + static_cast<uint32_t>(u1 - u0) * 2 * NSL;
                 // this CTA's share of the phase is done (merged outputs are counted by whoever merged them)
