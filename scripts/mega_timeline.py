@@ -1,7 +1,8 @@
 """Per-phase device timeline of the persistent decode-step kernel at the bench shape (830M, B=32), over ALL CTAs.
 Events per (cta, phase): 0 dep (B producer saw the previous phase complete), 1 acc (first accumulator of the phase ready),
-2 epi (this CTA finished a tile epilogue as last arriver), 3 end (this CTA's last segment handed over), 4 attention dep,
-5 attention loop end, 6 attention flag published, 7 ring producer issued the phase's last item.
+2 epi (this CTA finished a tile epilogue as last arriver), 3 end (this CTA's last segment handed over), 7 ring producer issued
+the phase's last item; GEMM phases: 4 B producer issued its last activation tile, 5 first MMA issued, 6 last MMA issued;
+attention phases: 4 dependency seen, 5 loop end, 6 flag published.
 usage: python scripts/mega_timeline.py [steps_before] [kv]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,10 +24,10 @@ nph = C.c_int32()
 _lib.check(lib.vcb_debug_mega_timeline(sess.eng, None, 0, C.byref(nph)))
 G = int(lib.vcb_counter(sess.eng, b"mega_grid"))
 for _ in range(3): sess.step()
-n = G * nph.value * 8
+n = G * nph.value * 16
 buf = (C.c_uint64 * n)()
 _lib.check(lib.vcb_debug_mega_timeline(sess.eng, buf, n, C.byref(nph)))
-t = np.frombuffer(buf, dtype=np.uint64).reshape(G, nph.value, 8).astype(np.float64)
+t = np.frombuffer(buf, dtype=np.uint64).reshape(G, nph.value, 16).astype(np.float64)
 t[t == 0] = np.nan
 t0 = np.nanmin(t[:, 0, :])
 t = (t - t0) / 1e3
@@ -39,7 +40,9 @@ for p in range(nph.value):
     if nm == "attn":
         print(f"{p:3d} {nm:5s} dep {f(t[:, p, 4])}  loop_end {f(t[:, p, 5])}  flag {f(t[:, p, 6])}  prod {f(t[:, p, 7])}")
     else:
-        print(f"{p:3d} {nm:5s} dep {f(t[:, p, 0])}  acc {f(t[:, p, 1])}  end {f(t[:, p, 3])}  epi {f(t[:, p, 2])}  prod {f(t[:, p, 7])}")
+        ep = t[:, p, 8:12] - t[:, p, 8:9]
+        print(f"        last-arriver path (us after arrival): operands {f(ep[:, 1])}  partials summed {f(ep[:, 2])}  stores issued {f(ep[:, 3])}  flag {f(t[:, p, 2] - t[:, p, 8])}")
+        print(f"{p:3d} {nm:5s} dep {f(t[:, p, 0])}  mma0 {f(t[:, p, 5])}  Blast {f(t[:, p, 4])}  mmaN {f(t[:, p, 6])}  acc {f(t[:, p, 1])}  end {f(t[:, p, 3])}  epi {f(t[:, p, 2])}  prod {f(t[:, p, 7])}")
 print("kernel span: %.1f us" % np.nanmax(t))
 # per-layer summary over the middle layers
 per = []

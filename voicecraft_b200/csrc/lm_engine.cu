@@ -1805,13 +1805,13 @@ int vcb_debug_exponential(float* out_dev, int64_t numel, uint64_t seed, uint64_t
 }
 
 // Debug timeline of the persistent decode-step kernel: the first call enables recording, later calls copy the last
-// step's records out: [grid CTAs][n_phases][8 events] %globaltimer ns (0 = event not recorded).
+// step's records out: [grid CTAs][n_phases][16 events] %globaltimer ns (0 = event not recorded).
 int vcb_debug_mega_timeline(vcb_engine* e, uint64_t* out_host, int32_t max_records, int32_t* n_phases) {
     if (!e || e->mega_grid <= 0) {
         set_error("persistent decode kernel not active");
         return -1;
     }
-    const size_t n = static_cast<size_t>(e->mega_grid) * e->mega_nph * 8;
+    const size_t n = static_cast<size_t>(e->mega_grid) * e->mega_nph * 16;
     if (!e->mega_tl) {
         VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->mega_tl), n * 8));
         VCB_CUDA_OK(cudaMemset(e->mega_tl, 0, n * 8));

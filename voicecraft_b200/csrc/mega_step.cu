@@ -42,6 +42,7 @@ static constexpr int MG_NACC = 4;              // TMEM accumulator stages
 static constexpr int MG_HD = 128;
 static constexpr int MG_PAGE = 64;
 static constexpr int MG_CHUNK = 4;             // attention: pages per work item (a chunk of one (row, head))
+static constexpr int MG_MAXCH = 16;            // chunks per item the in-CTA fold can hold (contexts up to 4096 tokens)
 static constexpr int MG_PSTR = 132;            // floats per page partial: acc[128], m, l, pad
 
 struct MegaSmem {
@@ -52,7 +53,8 @@ struct MegaSmem {
     static constexpr int TOTAL = MISC + 32 + 34 * 4 + 64;
     // attention scratch, aliased onto the B ring (idle during an attention phase)
     static constexpr int A_STATE = 0;                               // per-warp chunk states [8][MG_PSTR] floats
-    static constexpr int A_END = A_STATE + 8 * MG_PSTR * 4;
+    static constexpr int A_CHUNKS = A_STATE + 8 * MG_PSTR * 4;      // chunk states of the item in flight [MG_MAXCH][MG_PSTR]
+    static constexpr int A_END = A_CHUNKS + MG_MAXCH * MG_PSTR * 4;
 };
 static_assert(MegaSmem::A_END <= 3 * MG_BSLOT, "attention scratch must fit three B slots (nb >= 3)");
 static_assert(MegaSmem::TOTAL <= 232448, "shared memory budget of one CTA per SM");
@@ -156,7 +158,7 @@ __device__ __forceinline__ int mg_chunk_align(const int* s_cum, int H, int u, lo
 }
 // debug timeline: every CTA records %globaltimer at fixed (cta, phase, event) slots
 __device__ __forceinline__ void mg_tl(const MegaArgs& A, int p, int ev) {
-    if (A.tl != nullptr) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 8 + ev] = mg_now();
+    if (A.tl != nullptr) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + ev] = mg_now();
 }
 __device__ __forceinline__ int mg_owner(long long u, long long T, int G) { return static_cast<int>(((u + 1) * G - 1) / T); }
 
@@ -229,6 +231,7 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
             xold[rr] = __ldcg(reinterpret_cast<const float4*>(ep.x + static_cast<size_t>(row) * ep.ld_out + m0));
     }
     // ---- fixed-order sum of the partials (contributor = CTA order = ascending k) -------------------------------------------
+    if (A.tl != nullptr && wq == 0 && lane == 0 && bias[0] + mean[0] != 12345.678f) mg_tl(A, p, 9);   // operands / statistics landed
     float4 acc[RPW];
 #pragma unroll
     for (int rr = 0; rr < RPW; ++rr) acc[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -261,6 +264,7 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
             }
     }
     // ---- epilogue ---------------------------------------------------------------------------------------------------------
+    if (A.tl != nullptr && wq == 0 && lane == 0 && acc[0].x != 12345.678f) mg_tl(A, p, 10);    // after the reduction's loads landed
 #pragma unroll
     for (int rr = 0; rr < RPW; ++rr) {
         const int row = row_base + rr;
@@ -720,7 +724,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     }
                     mg_bar_workers();
                     if (*s_flag) {
+                        if (wtid == 0) mg_tl(A, p, 8);
                         mg_tile_epilogue<BPAD>(A, P, p, tile, c_first, ncontrib, T, Ge, wq, lane);
+                        if (wtid == 0) mg_tl(A, p, 11);
                         mg_bar_workers();
                         if (wtid == 0) {
                             A.tile_cnt[p * A.tile_cnt_stride + tile] = 0;
@@ -746,6 +752,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 // own context -- a row's tokens do not depend on what else is in the batch.
                 constexpr int LPT = MG_HD / 8, DPT = MG_HD / 32;
                 float* st_sm = reinterpret_cast<float*>(bring + L::A_STATE);         // [8 warps][MG_PSTR]
+                float* cs_sm = reinterpret_cast<float*>(bring + L::A_CHUNKS);        // [MG_MAXCH chunks of one item][MG_PSTR]
                 if (P.dep_target > 0) {
                     if (lane == 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 5, p);
                     __syncwarp();
@@ -879,7 +886,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[vs[j]]);
                         }
                     }
-                    // ---- chunk done: fold the 8 warp states in warp order ----------------------------------------------------------
+                    // ---- chunk done: fold the 8 warp states in warp order -> chunk state ---------------------------------------
                     {
                         float* ps = st_sm + wq * MG_PSTR;
                         *reinterpret_cast<float4*>(ps + lane * DPT) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -891,6 +898,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     mg_bar_workers();
                     const int n_chunks = (npg + MG_CHUNK - 1) / MG_CHUNK, cidx = pg / MG_CHUNK;
                     const size_t ocol = static_cast<size_t>(h) * MG_HD;
+                    const long long ui0 = static_cast<long long>(A.H) * s_cum[r] + static_cast<long long>(h) * npg;   // item's first unit
+                    const bool spans = ui0 < u0 || ui0 + static_cast<long long>(n_chunks - 1) * MG_CHUNK >= u1;        // chunks owned by other CTAs too
+                    const bool item_ends_here = pe == npg || u + (pe - pg) >= u1;   // my last chunk of this item
                     float* wsi = A.att_ws + static_cast<size_t>(rh) * A.max_pages * MG_PSTR;
                     if (wtid < MG_HD) {
                         float M = -INFINITY, Ls = 0.f, O = 0.f;
@@ -911,6 +921,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             split_bf16(o, hi, lo);
                             A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
                             A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                        } else if (!spans) {                                        // all chunks of the item are mine: keep it on chip
+                            cs_sm[cidx * MG_PSTR + wtid] = O;
+                            if (wtid == 0) {
+                                cs_sm[cidx * MG_PSTR + MG_HD] = M;
+                                cs_sm[cidx * MG_PSTR + MG_HD + 1] = Ls;
+                            }
                         } else {
                             __stcg(wsi + static_cast<size_t>(cidx) * MG_PSTR + wtid, O);
                             if (wtid == 0) {
@@ -919,35 +935,55 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             }
                         }
                     }
-                    if (n_chunks > 1) {
+                    if (n_chunks > 1 && item_ends_here) {
+                        // fold the item's chunk states in chunk order: from shared memory if they are all mine, else the
+                        // CTAs that own chunks of the item count in and the last one folds them from the workspace
+                        bool do_fold = true;
                         mg_bar_workers();
-                        if (wtid == 0) {
-                            __threadfence();
-                            *s_flag = (atomicAdd(A.att_cnt + rh, 1) == n_chunks - 1);
-                            __threadfence();
-                        }
-                        mg_bar_workers();
-                        if (*s_flag) {
-                            if (wtid < MG_HD) {
-                                float M = -INFINITY, Ls = 0.f, O = 0.f;
+                        if (spans) {
+                            if (wtid == 0) {
+                                int n_cta = 0, prev = -1;
                                 for (int j = 0; j < n_chunks; ++j) {
-                                    const float* ps = wsi + static_cast<size_t>(j) * MG_PSTR;
-                                    const float mp = __ldcg(ps + MG_HD), Mn = fmaxf(M, mp);
-                                    const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
-                                    Ls = Ls * c1 + __ldcg(ps + MG_HD + 1) * c2;
-                                    O = O * c1 + __ldcg(ps + wtid) * c2;
-                                    M = Mn;
+                                    const int o = mg_owner(ui0 + static_cast<long long>(j) * MG_CHUNK, U, Ue);
+                                    n_cta += o != prev;
+                                    prev = o;
                                 }
-                                const float o = O / Ls;
-                                __nv_bfloat16 hi, lo;
-                                split_bf16(o, hi, lo);
-                                A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                                A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                                __threadfence();
+                                *s_flag = (atomicAdd(A.att_cnt + rh, 1) == n_cta - 1);
+                                __threadfence();
                             }
-                            if (wtid == 0) A.att_cnt[rh] = 0;
+                            mg_bar_workers();
+                            do_fold = *s_flag != 0;
                         }
+                        if (do_fold && wtid < MG_HD) {
+                            float M = -INFINITY, Ls = 0.f, O = 0.f;
+                            for (int j = 0; j < n_chunks; ++j) {
+                                float mp, lp, op;
+                                if (spans) {
+                                    const float* ps = wsi + static_cast<size_t>(j) * MG_PSTR;
+                                    mp = __ldcg(ps + MG_HD);
+                                    lp = __ldcg(ps + MG_HD + 1);
+                                    op = __ldcg(ps + wtid);
+                                } else {
+                                    mp = cs_sm[j * MG_PSTR + MG_HD];
+                                    lp = cs_sm[j * MG_PSTR + MG_HD + 1];
+                                    op = cs_sm[j * MG_PSTR + wtid];
+                                }
+                                const float Mn = fmaxf(M, mp);
+                                const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
+                                Ls = Ls * c1 + lp * c2;
+                                O = O * c1 + op * c2;
+                                M = Mn;
+                            }
+                            const float o = O / Ls;
+                            __nv_bfloat16 hi, lo;
+                            split_bf16(o, hi, lo);
+                            A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
+                            A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                        }
+                        if (spans && do_fold && wtid == 0) A.att_cnt[rh] = 0;
                     }
-                    mg_bar_workers();                                               // warp states / s_flag are reused
+                    mg_bar_workers();                                               // warp / chunk states and s_flag are reused
                     u += pe - pg;
                 }
                 it = it0 + static_cast<uint32_t>(u1 - u0) * 2 * NSL;
