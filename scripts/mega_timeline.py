@@ -29,6 +29,8 @@ buf = (C.c_uint64 * n)()
 _lib.check(lib.vcb_debug_mega_timeline(sess.eng, buf, n, C.byref(nph)))
 t = np.frombuffer(buf, dtype=np.uint64).reshape(G, nph.value, 16).astype(np.float64)
 t[t == 0] = np.nan
+dur = t[:, :, 12:15].copy() / 1e3          # accumulated waits (us): 12 workers on full barriers, 13 producer on empty slots, 14 producer on the in-flight cap
+t[:, :, 12:15] = np.nan
 t0 = np.nanmin(t[:, 0, :])
 t = (t - t0) / 1e3
 names = ["qkv", "attn", "out", "ffn1", "ffn2"]
@@ -38,7 +40,7 @@ for p in range(nph.value):
     nm = names[p % 5] if p < nph.value - 2 else ("h1" if p == nph.value - 2 else "h2")
     if p >= 12 and p < nph.value - 7: continue
     if nm == "attn":
-        print(f"{p:3d} {nm:5s} dep {f(t[:, p, 4])}  loop_end {f(t[:, p, 5])}  flag {f(t[:, p, 6])}  prod {f(t[:, p, 7])}")
+        print(f"{p:3d} {nm:5s} dep {f(t[:, p, 4])}  loop_end {f(t[:, p, 5])}  flag {f(t[:, p, 6])}  prod {f(t[:, p, 7])}  | waits: workers on data {f(dur[:, p, 0])}  producer on free slots {f(dur[:, p, 1])}  on flight cap {f(dur[:, p, 2])}")
     else:
         ep = t[:, p, 8:12] - t[:, p, 8:9]
         print(f"        last-arriver path (us after arrival): operands {f(ep[:, 1])}  partials summed {f(ep[:, 2])}  stores issued {f(ep[:, 3])}  flag {f(t[:, p, 2] - t[:, p, 8])}")

@@ -131,7 +131,7 @@ struct vcb_engine {
     MegaPhase* d_mega_ph[2] = {nullptr, nullptr};
     CUtensorMap* d_wmaps = nullptr;        // device copies of the weight tensor maps: [L][qkv, out, ff1, ff2], h1
     const void** d_wptrs = nullptr;        // raw packed-weight pointers, same order, then the K second-stage head matrices
-    int mega_ns = 11, mega_nb = 6, mega_pf = 0;
+    int mega_ns = 11, mega_nb = 6, mega_pf = 0, mega_flight = 5;
     unsigned long long* mega_tl = nullptr;   // debug timeline of the persistent kernel (vcb_debug_mega_timeline)
     unsigned int* mega_flags = nullptr;
     int* mega_tile_cnt = nullptr;
@@ -764,6 +764,7 @@ int mega_setup(vcb_engine* e) {
         const long long T = static_cast<long long>(sh[0]) * sh[1];
         const long long per = (T + grid - 1) / grid;
         if ((per + sh[1] - 1) / sh[1] + 1 > MEGA_MAXSEG) return 0;
+        if (T * (grid + 1) >= (1ll << 31)) return 0;             // the kernel's work-split arithmetic is 32-bit
         max_tiles = std::max(max_tiles, sh[0]);
     }
     e->mega_cnt_stride = max_tiles;
@@ -803,6 +804,7 @@ int mega_setup(vcb_engine* e) {
     if (getenv("VCB_MEGA_NS")) e->mega_ns = atoi(getenv("VCB_MEGA_NS"));
     if (getenv("VCB_MEGA_NB")) e->mega_nb = atoi(getenv("VCB_MEGA_NB"));
     if (getenv("VCB_MEGA_PF")) e->mega_pf = atoi(getenv("VCB_MEGA_PF"));
+    if (getenv("VCB_MEGA_FLIGHT")) e->mega_flight = std::max(1, atoi(getenv("VCB_MEGA_FLIGHT")));
     if (e->mega_ns < 2 || e->mega_ns > 13 || e->mega_nb < 3 || e->mega_nb > 8 || e->mega_ns * 16384 + e->mega_nb * 8192 > 14 * 16384) {
         set_error("VCB_MEGA_NS / VCB_MEGA_NB: need 2 <= ns <= 13, 3 <= nb <= 8, ns * 16 KB + nb * 8 KB <= 224 KB");
         return -1;
@@ -828,6 +830,7 @@ int mega_step(vcb_engine* e, int n, cudaStream_t st) {
     a.ns = e->mega_ns;
     a.nb = e->mega_nb;
     a.pf = e->mega_pf;
+    a.flight = e->mega_flight;
     a.flags = e->mega_flags;
     a.tile_cnt = e->mega_tile_cnt;
     a.tile_cnt_stride = e->mega_cnt_stride;

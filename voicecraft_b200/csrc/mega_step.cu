@@ -130,14 +130,16 @@ __device__ __forceinline__ void mg_wait_issued(volatile uint32_t* s_prod, uint32
 
 // Work split of T units over the first Ge = min(G, T) CTAs (every one of them gets >= 1 unit, the others none, so the
 // CTAs that share a tile / an attention item are always consecutive): range of CTA c, and the CTA that owns unit u.
+// (32-bit arithmetic: the host checks T * G < 2^31; 64-bit divisions are ~10x slower and sit on every role's path)
 __device__ __forceinline__ int mg_eff(long long T, int G) { return static_cast<int>(T < G ? T : G); }
 __device__ __forceinline__ void mg_range(long long T, int c, int Ge, int& b0, int& b1) {
     if (c >= Ge) {
         b0 = b1 = 0;
         return;
     }
-    b0 = static_cast<int>(T * c / Ge);
-    b1 = static_cast<int>(T * (c + 1) / Ge);
+    const unsigned int t = static_cast<unsigned int>(T), g = static_cast<unsigned int>(Ge), cc = static_cast<unsigned int>(c);
+    b0 = static_cast<int>(t * cc / g);
+    b1 = static_cast<int>(t * (cc + 1u) / g);
 }
 // attention unit u -> (row, head, page) and the row's page count; units are ordered (row, head, page)
 __device__ __forceinline__ void mg_locate(const int* s_cum, int H, int u, int& r, int& h, int& pg, int& npg) {
@@ -160,7 +162,9 @@ __device__ __forceinline__ int mg_chunk_align(const int* s_cum, int H, int u, lo
 __device__ __forceinline__ void mg_tl(const MegaArgs& A, int p, int ev) {
     if (A.tl != nullptr) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + ev] = mg_now();
 }
-__device__ __forceinline__ int mg_owner(long long u, long long T, int G) { return static_cast<int>(((u + 1) * G - 1) / T); }
+__device__ __forceinline__ int mg_owner(long long u, long long T, int G) {
+    return static_cast<int>(((static_cast<unsigned int>(u) + 1u) * static_cast<unsigned int>(G) - 1u) / static_cast<unsigned int>(T));
+}
 
 __device__ __forceinline__ uint2 mg_pack_bf16x4(float a, float b, float c, float d) {
     const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
@@ -243,7 +247,7 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
             const int s = s0 + j;
             if (s < ncontrib) {
                 const int c = c_first + s;
-                const int cb0 = static_cast<int>(T * c / G);
+                const int cb0 = static_cast<int>(static_cast<unsigned int>(T) * static_cast<unsigned int>(c) / static_cast<unsigned int>(G));
                 const int seg = tile - cb0 / kb;
                 const float* src = A.part + (static_cast<size_t>(c) * MEGA_MAXSEG + seg) * BPAD * 128 + 4 * lane;
 #pragma unroll
@@ -465,10 +469,29 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
         // ===== ring producer: weight blocks and K/V slabs of every phase, in schedule order ==============================
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
-            uint32_t it = 0;
+            uint32_t it = 0, landed = 0;
+            const uint32_t flight = static_cast<uint32_t>(A.flight);
+            unsigned long long wait_empty_ns = 0, wait_flight_ns = 0;
             auto acquire = [&](int p) -> int {
                 const int s = it % MG_NS;
+                unsigned long long tw0 = 0;
+                if (A.tl != nullptr) tw0 = mg_now();
                 if (it >= MG_NS) mg_wait(&empty[s], ((it / MG_NS) - 1) & 1, A.dbg, 0, p);
+                if (A.tl != nullptr) {
+                    const unsigned long long t1 = mg_now();
+                    wait_empty_ns += t1 - tw0;
+                    tw0 = t1;
+                }
+                // Bound the loads IN FLIGHT (issued, not landed), not just the ring's capacity: this SM's memory pipe serves
+                // requests roughly in order, so the activation tiles / partials a phase hand-over is waiting for queue behind
+                // whatever the ring still has outstanding (11 x 16 KB at this SM's ~44 GB/s HBM share = 4 us of backlog;
+                // measured as ~0.6 us per activation tile).  `flight` x 16 KB keeps HBM saturated (Little: ~45 KB per SM)
+                // while landed slots still pile up to the ring's depth during a dependency chain.
+                while (it - landed >= flight) {
+                    mg_wait(&full[landed % MG_NS], (landed / MG_NS) & 1, A.dbg, 9, p);
+                    ++landed;
+                }
+                if (A.tl != nullptr) wait_flight_ns += mg_now() - tw0;
                 ++it;
                 *s_prod = it;
                 return s;
@@ -522,6 +545,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     }
                 }
                 mg_tl(A, p, 7);
+                if (A.tl != nullptr) {
+                    A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + 13] = wait_empty_ns + 1;
+                    A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + 14] = wait_flight_ns + 1;
+                    wait_empty_ns = wait_flight_ns = 0;
+                }
             }
         }
     } else if (warp == 1) {
@@ -760,6 +788,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 if (wtid == 0) mg_tl(A, p, 4);
                 const int sub = lane % LPT, half = lane / LPT;
                 const uint32_t it0 = it;
+                unsigned long long wait_full_ns = 0;
                 // operands of a chunk that come from this step's QKV epilogue: q, and the current position's k / v if the chunk
                 // holds it.  Loaded one chunk ahead (L2 round trip off the critical path).
                 auto fetch = [&](int u, float (&q8)[8], float (&k8)[8], float (&v4)[DPT]) {
@@ -811,8 +840,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             vs[j] = (itu + NSL + j) % MG_NS;
                         }
                         const int self_t = (pgi == npg - 1) ? pos - pgi * MG_PAGE : -1;
+                        unsigned long long tw0 = 0;
+                        if (A.tl != nullptr && wtid == 0) tw0 = mg_now();
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((itu + j) / MG_NS) & 1, A.dbg, 6, p);
+                        if (A.tl != nullptr && wtid == 0) wait_full_ns += mg_now() - tw0;
                         // ---- scores of my 8 keys: 2 per iteration (one per half-warp), xor-reduce inside the half-warp
                         float sc[4];
 #pragma unroll
@@ -859,8 +891,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
 #pragma unroll
                         for (int i = 0; i < DPT; ++i) acc[i] *= corr;
                         // ---- PV over my 8 keys
+                        if (A.tl != nullptr && wtid == 0) tw0 = mg_now();
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((itu + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
+                        if (A.tl != nullptr && wtid == 0) wait_full_ns += mg_now() - tw0;
 #pragma unroll
                         for (int itq = 0; itq < 4; ++itq) {
                             const float po = __shfl_xor_sync(0xffffffffu, pr[itq], 16);
@@ -989,6 +1023,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 it = it0 + static_cast<uint32_t>(u1 - u0) * 2 * NSL;
                 // this CTA's share of the phase is done (merged outputs are counted by whoever merged them)
                 if (wtid == 0) mg_tl(A, p, 5);
+                if (A.tl != nullptr && wtid == 0) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + 12] = wait_full_ns + 1;
                 __threadfence();
                 mg_bar_workers();
                 if (wtid == 0) {

@@ -93,6 +93,7 @@ struct MegaArgs {
     int nph = 0, nvalid = 0, bpad = 0, kv_fp32 = 0;
     int ns = 11, nb = 6;                // ring depths: ns * 16 KB + nb * 8 KB <= 224 KB
     int pf = 0;                         // L2 prefetch distance in ring items (0 = off)
+    int flight = 5;                     // ring loads in flight (issued, not landed) per SM
     unsigned int* flags = nullptr;      // [nph] completion counters (zeroed by step_prep)
     int* tile_cnt = nullptr;            // [nph][max tiles] split-K arrival counters (self-resetting)
     int tile_cnt_stride = 0;
