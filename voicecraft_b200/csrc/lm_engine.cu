@@ -741,6 +741,18 @@ int mega_build(vcb_engine* e, int bpad) {
     h2.done_target = m.K * h2.tiles_per_group;
     h2.ep.mode = EPI_LOGITS; h2.ep.out = e->logits; h2.ep.ld_out = m.K * m.Vpad; h2.ep.col_off = 0;
     ph.push_back(h2);
+    // a GEMM phase is complete when every (tile, contributing CTA) pair has run its share of the tile's epilogue
+    for (auto& P : ph) {
+        if (P.type != MEGA_GEMM) continue;
+        const long long T = static_cast<long long>(P.groups) * P.tiles_per_group * P.kb;
+        const int Ge = static_cast<int>(std::min<long long>(e->mega_grid, T));
+        int segs = 0;
+        for (int c = 0; c < Ge; ++c) {
+            const long long b0 = T * c / Ge, b1 = T * (c + 1) / Ge;
+            segs += static_cast<int>((b1 - 1) / P.kb - b0 / P.kb + 1);
+        }
+        P.done_target = segs;
+    }
     for (size_t i = 1; i < ph.size(); ++i) ph[i].dep_target = ph[i - 1].done_target;
     e->mega_nph = static_cast<int>(ph.size());
     if (!e->d_mega_ph[which]) VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_mega_ph[which]), ph.size() * sizeof(MegaPhase)));
@@ -1511,7 +1523,8 @@ int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float*
                              e->row_pos, e->row_last, e->x_slot, e->x_rows, e->m.d,
                              fold ? e->layers[0].ln1_g : static_cast<const float*>(nullptr), e->act_d, bpad_for(n),
                              e->ln_stats, e->page_table, e->max_pages_per_slot, e->row_page, e->row_pages, e->row_forced,
-                             e->mega_flags, e->mega_flags ? e->mega_nph : 0));
+                             e->mega_flags, e->mega_flags ? e->mega_nph : 0, reinterpret_cast<unsigned int*>(e->mega_tile_cnt),
+                             e->mega_flags ? e->mega_nph * e->mega_cnt_stride : 0));
     }
     LAUNCH_COUNT(e);
     e->cur_slot = e->row_slot;

@@ -412,13 +412,15 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
                  const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats,
                  const int* __restrict__ page_table, int max_pages, int* __restrict__ row_page,
                  int* __restrict__ row_pages, int* __restrict__ row_forced, unsigned int* __restrict__ phase_flags,
-                 int n_phase_flags) {
+                 int n_phase_flags, unsigned int* __restrict__ tile_counters, int n_tile_counters) {
     __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x;
     if (r == 0)                                  // completion counters of the persistent step kernel (mega_step.cu)
         for (int i = threadIdx.x; i < n_phase_flags; i += blockDim.x) phase_flags[i] = 0u;
+    // ... and its split-K arrival counters, spread over the CTAs of this launch
+    for (int i = r * blockDim.x + threadIdx.x; i < n_tile_counters; i += gridDim.x * blockDim.x) tile_counters[i] = 0u;
     const int slot = slots[r];
     __shared__ int s_pos;
     if (threadIdx.x == 0) {

@@ -54,7 +54,8 @@ struct MegaSmem {
     // attention scratch, aliased onto the B ring (idle during an attention phase)
     static constexpr int A_STATE = 0;                               // per-warp chunk states [8][MG_PSTR] floats
     static constexpr int A_CHUNKS = A_STATE + 8 * MG_PSTR * 4;      // chunk states of the item in flight [MG_MAXCH][MG_PSTR]
-    static constexpr int A_END = A_CHUNKS + MG_MAXCH * MG_PSTR * 4;
+    static constexpr int A_Q = A_CHUNKS + MG_MAXCH * MG_PSTR * 4;   // q * scale * log2(e) of this / the next chunk [2][128]
+    static constexpr int A_END = A_Q + 2 * MG_HD * 4;
 };
 static_assert(MegaSmem::A_END <= 3 * MG_BSLOT, "attention scratch must fit three B slots (nb >= 3)");
 static_assert(MegaSmem::TOTAL <= 232448, "shared memory budget of one CTA per SM");
@@ -176,121 +177,120 @@ __device__ __forceinline__ uint2 mg_pack_bf16x4(float a, float b, float c, float
 __device__ __forceinline__ float mg_bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Fused epilogue of one output tile, run by the 256 worker threads of the CTA that arrived last.
-// Thread mapping: lane -> features 4*lane .. 4*lane+3 of the tile, warp wq -> rows wq*RPW .. wq*RPW+RPW-1.
+// Split-K hand-over of one output tile, reduce-scatter through L2: every CTA that contributed a partial of the tile
+// ("contributor" s = 0 .. S-1 in CTA order = ascending k) takes the token rows [s*BPAD/S, (s+1)*BPAD/S), sums the S partials
+// of those rows in contributor order (deterministic) and runs the fused epilogue on them.  (A single "last arriver"
+// reading all S x 16 KB through one SM's L2 port was measured at 3.5 us for S = 10.)
+// Thread mapping: lane -> features 4*lane .. 4*lane+3 of the tile; warp wq -> rows row_begin + wq + 8j.
+// mg_epi_prefetch loads everything that does not depend on the other contributors (issued BEFORE waiting for them).
 // ------------------------------------------------------------------------------------------------------------------------
 template <int BPAD>
-__device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPhase& P, int p, int tile, int c_first, int ncontrib,
-                                                 long long T, int G, int wq, int lane) {
-    constexpr int RPW = BPAD / 8;
-    // The descriptor is copied into registers / local memory ONCE: read through a reference into global memory, every field
-    // would be re-loaded after each of the epilogue's global stores (possible aliasing), and the per-row position / page
-    // look-ups would become chains of dependent L2 round trips between the stores (measured: ~9 us per tile).
-    const GemmEpilogue ep = P.ep;
-    const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
-    const int m0 = tl * 128 + 4 * lane;                       // first of my 4 features (group-local)
-    const int Nout = P.Nout;
-    const int row_base = wq * RPW;
-    const int col_grp = g * P.col_grp_stride;
-    int rpos[RPW], rpage[RPW];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-        const int row = row_base + rr;
-        const bool live = ep.mode == EPI_QKV && row < A.nvalid;
-        rpos[rr] = live ? ep.row_pos[row] : -1;
-        rpage[rr] = live ? ep.row_page[row] : 0;
-    }
-    // ---- operands that do not depend on the reduction ------------------------------------------------------------------
-    const float* bias_ptr = P.grp_bias ? P.grp_bias[g] : ep.bias;
+struct MgEpiRegs {
+    static constexpr int MAXR = BPAD / 8;
     float bias[4], cv[4], gn[4];
+    float mean[MAXR], rstd[MAXR];
+    float4 xold[MAXR];
+    int rpos[MAXR], rpage[MAXR];
+};
+
+template <int BPAD>
+__device__ __forceinline__ void mg_epi_prefetch(const MegaArgs& A, const MegaPhase& P, const GemmEpilogue& ep, int tile, int row_begin,
+                                                int row_end, int wq, int lane, MgEpiRegs<BPAD>& R) {
+    constexpr int MAXR = BPAD / 8;
+    const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
+    const int m0 = tl * 128 + 4 * lane;
+    const int Nout = P.Nout;
+    const float* bias_ptr = P.grp_bias ? P.grp_bias[g] : ep.bias;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const bool ok = m0 + i < Nout;
-        bias[i] = ok ? bias_ptr[m0 + i] : 0.f;
-        cv[i] = (ok && ep.ln_fold) ? ep.cvec[m0 + i] : 0.f;
-        gn[i] = (ok && ep.emit) ? ep.next_gamma[m0 + i] : 0.f;
+        R.bias[i] = ok ? bias_ptr[m0 + i] : 0.f;
+        R.cv[i] = (ok && ep.ln_fold) ? ep.cvec[m0 + i] : 0.f;
+        R.gn[i] = (ok && ep.emit) ? ep.next_gamma[m0 + i] : 0.f;
     }
-    float mean[RPW], rstd[RPW];
-    float4 xold[RPW];
 #pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-        const int row = row_base + rr;
-        mean[rr] = 0.f;
-        rstd[rr] = 0.f;
-        xold[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.ln_fold) {
+    for (int j = 0; j < MAXR; ++j) {
+        const int row = row_begin + wq + 8 * j;
+        const bool live = row < row_end && row < A.nvalid;          // warp-uniform
+        R.mean[j] = 0.f;
+        R.rstd[j] = 0.f;
+        R.xold[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.rpos[j] = (live && ep.mode == EPI_QKV) ? ep.row_pos[row] : -1;
+        R.rpage[j] = (live && ep.mode == EPI_QKV) ? ep.row_page[row] : 0;
+        if (ep.ln_fold && live) {
             float s1 = 0.f, s2 = 0.f;
-            if (row < A.nvalid)
-                for (int t = lane; t < ep.stats_tiles; t += 32) {
-                    const float2 v = __ldcg(reinterpret_cast<const float2*>(ep.stats + (static_cast<size_t>(t) * STATS_ROWS + row) * 2));
-                    s1 += v.x;
-                    s2 += v.y;
-                }
+            for (int t = lane; t < ep.stats_tiles; t += 32) {
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(ep.stats + (static_cast<size_t>(t) * STATS_ROWS + row) * 2));
+                s1 += v.x;
+                s2 += v.y;
+            }
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
-            mean[rr] = s1 * ep.inv_d;
-            rstd[rr] = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - mean[rr] * mean[rr], 0.f) + ep.ln_eps);
+            R.mean[j] = s1 * ep.inv_d;
+            R.rstd[j] = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - R.mean[j] * R.mean[j], 0.f) + ep.ln_eps);
         }
-        if (ep.mode == EPI_RESID && row < A.nvalid)
-            xold[rr] = __ldcg(reinterpret_cast<const float4*>(ep.x + static_cast<size_t>(row) * ep.ld_out + m0));
+        if (ep.mode == EPI_RESID && live && m0 < Nout)
+            R.xold[j] = __ldcg(reinterpret_cast<const float4*>(ep.x + static_cast<size_t>(row) * ep.ld_out + m0));
     }
-    // ---- fixed-order sum of the partials (contributor = CTA order = ascending k) -------------------------------------------
-    if (A.tl != nullptr && wq == 0 && lane == 0 && bias[0] + mean[0] != 12345.678f) mg_tl(A, p, 9);   // operands / statistics landed
-    float4 acc[RPW];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) acc[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int BPAD>
+__device__ __forceinline__ void mg_epi_finish(const MegaArgs& A, const MegaPhase& P, const GemmEpilogue& ep, int p, int tile, int c_first,
+                                              int ncontrib, long long T, int G, int row_begin, int row_end, int wq, int lane,
+                                              const MgEpiRegs<BPAD>& R) {
+    constexpr int MAXR = BPAD / 8;
+    const int g = tile / P.tiles_per_group, tl = tile - g * P.tiles_per_group;
+    const int m0 = tl * 128 + 4 * lane;
+    const int Nout = P.Nout;
+    const int col_grp = g * P.col_grp_stride;
     const int kb = P.kb;
-    for (int s0 = 0; s0 < ncontrib; s0 += 4) {
-        float4 v[4][RPW];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int s = s0 + j;
-            if (s < ncontrib) {
-                const int c = c_first + s;
-                const int cb0 = static_cast<int>(static_cast<unsigned int>(T) * static_cast<unsigned int>(c) / static_cast<unsigned int>(G));
-                const int seg = tile - cb0 / kb;
-                const float* src = A.part + (static_cast<size_t>(c) * MEGA_MAXSEG + seg) * BPAD * 128 + 4 * lane;
+    for (int j = 0; j < MAXR; ++j) {
+        const int row = row_begin + wq + 8 * j;
+        if (row >= row_end) break;                                    // warp-uniform
+        const bool row_ok = row < A.nvalid;
+        // ---- fixed-order sum of the S partials of this row --------------------------------------------------------------------
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < ncontrib; s0 += 8) {
+            float4 v[8];
 #pragma unroll
-                for (int rr = 0; rr < RPW; ++rr) v[j][rr] = __ldcg(reinterpret_cast<const float4*>(src + (row_base + rr) * 128));
-            } else {
+            for (int u = 0; u < 8; ++u) {
+                const int s = s0 + u;
+                if (s < ncontrib) {
+                    const int c = c_first + s;
+                    const int cb0 = static_cast<int>(static_cast<unsigned int>(T) * static_cast<unsigned int>(c) / static_cast<unsigned int>(G));
+                    const float* src = A.part + ((static_cast<size_t>(c) * MEGA_MAXSEG + (tile - cb0 / kb)) * BPAD + row) * 128 + 4 * lane;
+                    v[u] = __ldcg(reinterpret_cast<const float4*>(src));
+                } else {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
 #pragma unroll
-                for (int rr = 0; rr < RPW; ++rr) v[j][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < 8; ++u) {
+                acc.x += v[u].x;
+                acc.y += v[u].y;
+                acc.z += v[u].z;
+                acc.w += v[u].w;
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int rr = 0; rr < RPW; ++rr) {
-                acc[rr].x += v[j][rr].x;
-                acc[rr].y += v[j][rr].y;
-                acc[rr].z += v[j][rr].z;
-                acc[rr].w += v[j][rr].w;
-            }
-    }
-    // ---- epilogue ---------------------------------------------------------------------------------------------------------
-    if (A.tl != nullptr && wq == 0 && lane == 0 && acc[0].x != 12345.678f) mg_tl(A, p, 10);    // after the reduction's loads landed
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-        const int row = row_base + rr;
-        const bool row_ok = row < A.nvalid;                   // warp-uniform
-        float a[4] = {acc[rr].x, acc[rr].y, acc[rr].z, acc[rr].w};
+        float a[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (ep.ln_fold) a[i] = rstd[rr] * (a[i] - mean[rr] * cv[i]);
-            a[i] += bias[i];
+            if (ep.ln_fold) a[i] = R.rstd[j] * (a[i] - R.mean[j] * R.cv[i]);
+            a[i] += R.bias[i];
         }
         float xn[4] = {0.f, 0.f, 0.f, 0.f};
         if (row_ok) {
             switch (ep.mode) {
                 case EPI_QKV: {
-                    const int pos = rpos[rr];
+                    const int pos = R.rpos[j];
                     if (pos < 0 || m0 >= Nout) break;
                     const int part = m0 / ep.d, cc = m0 - part * ep.d;
                     if (part == 0) {
                         __stcg(reinterpret_cast<float4*>(ep.qbuf + static_cast<size_t>(row) * ep.d + cc), make_float4(a[0], a[1], a[2], a[3]));
                         break;
                     }
-                    const int page = rpage[rr];
+                    const int page = R.rpage[j];
                     const int h = cc / ep.hd, e = cc - h * ep.hd;
                     const size_t off = ((static_cast<size_t>(page) * ep.H + h) * ep.page_size + pos % ep.page_size) * ep.hd + e;
                     void* pool = (part == 1) ? ep.kpool : ep.vpool;
@@ -306,10 +306,10 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
                     break;
                 }
                 case EPI_RESID: {
-                    xn[0] = xold[rr].x + a[0];
-                    xn[1] = xold[rr].y + a[1];
-                    xn[2] = xold[rr].z + a[2];
-                    xn[3] = xold[rr].w + a[3];
+                    xn[0] = R.xold[j].x + a[0];
+                    xn[1] = R.xold[j].y + a[1];
+                    xn[2] = R.xold[j].z + a[2];
+                    xn[3] = R.xold[j].w + a[3];
                     if (m0 < Nout)
                         __stcg(reinterpret_cast<float4*>(ep.x + static_cast<size_t>(row) * ep.ld_out + m0), make_float4(xn[0], xn[1], xn[2], xn[3]));
                     break;
@@ -350,7 +350,7 @@ __device__ __forceinline__ void mg_tile_epilogue(const MegaArgs& A, const MegaPh
                 float hi[4], lo[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float v = gn[i] * xn[i];
+                    const float v = R.gn[i] * xn[i];
                     hi[i] = mg_bf16_round(v);
                     lo[i] = v - hi[i];
                     p1 += xn[i];
@@ -739,81 +739,72 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     float* pdst = A.part + (static_cast<size_t>(cta) * MEGA_MAXSEG + (tile - first_tile)) * BPAD * 128 + ml;
 #pragma unroll
                     for (int j = 0; j < HB; ++j) __stcg(pdst + (grp * HB + j) * 128, v[j]);
-                    // release: the block barrier orders every worker's stores before thread 0's GPU-scope fence (fences are
-                    // cumulative), the atomic publishes; acquire: thread 0's fence after the atomic, then the barrier
+                    // hand-over: publish my partial (the block barrier orders every worker's stores before thread 0's GPU-scope
+                    // fence -- fences are cumulative), count in, fetch my rows' epilogue operands WHILE the other contributors
+                    // arrive, then reduce + epilogue my share of the tile's rows
                     mg_bar_workers();
                     const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, Ge);
                     const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, Ge);
                     const int ncontrib = c_last - c_first + 1;
+                    const int sidx = cta - c_first;
+                    const int row_begin = sidx * BPAD / ncontrib, row_end = (sidx + 1) * BPAD / ncontrib;
+                    int* cnt = A.tile_cnt + p * A.tile_cnt_stride + tile;
                     if (wtid == 0) {
                         __threadfence();
-                        *s_flag = (atomicAdd(A.tile_cnt + p * A.tile_cnt_stride + tile, 1) == ncontrib - 1);
-                        __threadfence();
+                        atomicAdd(cnt, 1);
+                    }
+                    const GemmEpilogue ep = P.ep;           // by value: no re-loads of its fields between the epilogue's stores
+                    MgEpiRegs<BPAD> R;
+                    mg_epi_prefetch<BPAD>(A, P, ep, tile, row_begin, row_end, wq, lane, R);
+                    if (wtid == 0) {
+                        mg_wait_flag(reinterpret_cast<const unsigned int*>(cnt), static_cast<unsigned int>(ncontrib), A.dbg, 10, p);
+                        mg_tl(A, p, 8);
                     }
                     mg_bar_workers();
-                    if (*s_flag) {
-                        if (wtid == 0) mg_tl(A, p, 8);
-                        mg_tile_epilogue<BPAD>(A, P, p, tile, c_first, ncontrib, T, Ge, wq, lane);
-                        if (wtid == 0) mg_tl(A, p, 11);
-                        mg_bar_workers();
-                        if (wtid == 0) {
-                            A.tile_cnt[p * A.tile_cnt_stride + tile] = 0;
-                            __threadfence();
-                            mg_fence_proxy_async();
-                            atomicAdd(A.flags + p, 1u);
-                            mg_tl(A, p, 2);
-                        }
-                    } else {
-                        mg_bar_workers();                 // s_flag is rewritten by the next tile
+                    mg_epi_finish<BPAD>(A, P, ep, p, tile, c_first, ncontrib, T, Ge, row_begin, row_end, wq, lane, R);
+                    mg_bar_workers();
+                    if (wtid == 0) {
+                        __threadfence();
+                        mg_fence_proxy_async();
+                        atomicAdd(A.flags + p, 1u);
+                        mg_tl(A, p, 2);
                     }
                     if (wtid == 0) mg_tl(A, p, 3);
                 }
             } else {
                 // ===== attention: units [u0, u1), cut at chunk boundaries ======================================================
                 // Work item = CHUNK of up to MG_CHUNK consecutive pages of one (row, head); the chunk grid depends only on the
-                // row's own context length.  The 8 worker warps share every page: warp w scores keys [8w, 8w+8) of the page,
+                // row's own context length.  The 8 worker warps share every page: warp w owns keys [8w, 8w+8) of the page,
                 // keeps its own online-softmax state (m, l, acc) over the chunk's pages and multiplies its 8 probabilities
-                // into V -- no block barrier per page, so a K/V slab leaves the ring ~0.3 us after it lands (the ring's
-                // residence time, not the math, bounds the HBM stream).  Per chunk: the 8 warp states fold in warp order,
-                // a one-chunk item goes out directly, otherwise the chunk state is published and the last chunk to arrive
-                // folds all chunk states in chunk order.  Every result is a fixed-order fold that depends only on the row's
-                // own context -- a row's tokens do not depend on what else is in the batch.
-                constexpr int LPT = MG_HD / 8, DPT = MG_HD / 32;
+                // into V -- no block barrier per page.  Per chunk the 8 warp states fold in warp order, chunks fold in chunk
+                // order: every result is a fixed-order fold that depends only on the row's own context (a row's tokens do
+                // not depend on what else is in the batch).
+                // The page loop is ISSUE-bound on CUDA cores (measured: ~650 SASS instructions per page and warp took 1.5 us
+                // per page, twice the HBM time of the page), so it is written for instruction count:
+                //   * 4 lanes per key (32 dims each): one pass of 4 x LDS.128 + 32 FMA covers the warp's 8 keys, 2 shuffles
+                //   * scores in the log2 domain: q is staged once per chunk as q * (scale * log2 e), probabilities are exp2
+                //   * the current position's key / value (from this step's QKV epilogue, not from the page) is ONE extra key
+                //     folded in by warp 0 after the last page -- no per-element selects inside the loop
+                constexpr int DPT = MG_HD / 32;
                 float* st_sm = reinterpret_cast<float*>(bring + L::A_STATE);         // [8 warps][MG_PSTR]
                 float* cs_sm = reinterpret_cast<float*>(bring + L::A_CHUNKS);        // [MG_MAXCH chunks of one item][MG_PSTR]
+                float* q_sm = reinterpret_cast<float*>(bring + L::A_Q);              // [2][MG_HD]: this / the next chunk's q'
                 if (P.dep_target > 0) {
                     if (lane == 0) mg_wait_flag(A.flags + (p - 1), P.dep_target, A.dbg, 5, p);
                     __syncwarp();
                 }
                 if (wtid == 0) mg_tl(A, p, 4);
-                const int sub = lane % LPT, half = lane / LPT;
+                const int kj = lane >> 2, qc = lane & 3;                             // my key inside the warp's slice, my dim quarter
                 const uint32_t it0 = it;
                 unsigned long long wait_full_ns = 0;
-                // operands of a chunk that come from this step's QKV epilogue: q, and the current position's k / v if the chunk
-                // holds it.  Loaded one chunk ahead (L2 round trip off the critical path).
-                auto fetch = [&](int u, float (&q8)[8], float (&k8)[8], float (&v4)[DPT]) {
+                const float qscale = A.scale * 1.4426950408889634f;
+                int qbuf_sel = 0;
+                if (u0 < u1 && wtid < MG_HD) {                                        // first chunk's q (exposed once per phase)
                     int r, h, pg, npg;
-                    mg_locate(s_cum, A.H, u, r, h, pg, npg);
-                    const size_t base = (static_cast<size_t>(r) * A.H + h) * MG_HD;
-                    const float4* qp = reinterpret_cast<const float4*>(A.qbuf + base + sub * 8);
-                    const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
-                    q8[0] = q0.x; q8[1] = q0.y; q8[2] = q0.z; q8[3] = q0.w;
-                    q8[4] = q1.x; q8[5] = q1.y; q8[6] = q1.z; q8[7] = q1.w;
-                    if (pg + MG_CHUNK >= npg) {                                      // the chunk holds the row's last page
-                        const float4* kp = reinterpret_cast<const float4*>(A.knew + base + sub * 8);
-                        const float4 k0 = __ldcg(kp), k1 = __ldcg(kp + 1);
-                        k8[0] = k0.x; k8[1] = k0.y; k8[2] = k0.z; k8[3] = k0.w;
-                        k8[4] = k1.x; k8[5] = k1.y; k8[6] = k1.z; k8[7] = k1.w;
-                        const float4 v0 = __ldcg(reinterpret_cast<const float4*>(A.vnew + base + lane * DPT));
-                        v4[0] = v0.x; v4[1] = v0.y; v4[2] = v0.z; v4[3] = v0.w;
-                    }
-                };
-                float qn[8], kn[8], vn[DPT];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) qn[i] = kn[i] = 0.f;
-#pragma unroll
-                for (int i = 0; i < DPT; ++i) vn[i] = 0.f;
-                if (u0 < u1) fetch(u0, qn, kn, vn);
+                    mg_locate(s_cum, A.H, u0, r, h, pg, npg);
+                    q_sm[wtid] = __ldcg(A.qbuf + (static_cast<size_t>(r) * A.H + h) * MG_HD + wtid) * qscale;
+                }
+                mg_bar_workers();
                 int u = u0;
                 while (u < u1) {
                     int r, h, pg, npg;
@@ -821,16 +812,38 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     const int pe = min(npg, pg + MG_CHUNK);
                     const int pos = A.row_pos[r];
                     const int rh = r * A.H + h;
-                    float qv[8], kself[8], vself[DPT];
+                    const bool has_self = pe == npg;                                 // the chunk ends at the current position
+                    // operands fetched now, used after the page loop: next chunk's q (threads < 128), my slice of k_new / v_new
+                    float q_next = 0.f;
+                    const int un = u + (pe - pg);
+                    if (un < u1 && wtid < MG_HD) {
+                        int r2, h2, pg2, npg2;
+                        mg_locate(s_cum, A.H, un, r2, h2, pg2, npg2);
+                        q_next = __ldcg(A.qbuf + (static_cast<size_t>(r2) * A.H + h2) * MG_HD + wtid);
+                    }
+                    float4 kself4 = make_float4(0.f, 0.f, 0.f, 0.f), vself4 = kself4;
+                    if (has_self && wq == 0) {
+                        kself4 = __ldcg(reinterpret_cast<const float4*>(A.knew + static_cast<size_t>(rh) * MG_HD + lane * DPT));
+                        vself4 = __ldcg(reinterpret_cast<const float4*>(A.vnew + static_cast<size_t>(rh) * MG_HD + lane * DPT));
+                    }
+                    // my 32 dims of q': dims [i*32 + qc*8, +8), i = 0..3 (the same split the K loads use: 16-byte chunks of
+                    // the 4 lanes of a key are adjacent, so a quarter-warp's LDS.128 touches distinct banks)
+                    float qv[32];
+                    {
+                        const float* qs = q_sm + qbuf_sel * MG_HD;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { qv[i] = qn[i]; kself[i] = kn[i]; }
-#pragma unroll
-                    for (int i = 0; i < DPT; ++i) vself[i] = vn[i];
-                    if (u + (pe - pg) < u1) fetch(u + (pe - pg), qn, kn, vn);       // next chunk's operands
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 a0 = *reinterpret_cast<const float4*>(qs + i * 32 + qc * 8);
+                            const float4 a1 = *reinterpret_cast<const float4*>(qs + i * 32 + qc * 8 + 4);
+                            qv[i * 8 + 0] = a0.x; qv[i * 8 + 1] = a0.y; qv[i * 8 + 2] = a0.z; qv[i * 8 + 3] = a0.w;
+                            qv[i * 8 + 4] = a1.x; qv[i * 8 + 5] = a1.y; qv[i * 8 + 6] = a1.z; qv[i * 8 + 7] = a1.w;
+                        }
+                    }
                     float m_run = -INFINITY, l_run = 0.f;
                     float acc[DPT];
 #pragma unroll
                     for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+                    const int t_key = wq * 8 + kj;                                   // my key inside the page
                     for (int pgi = pg; pgi < pe; ++pgi) {
                         const uint32_t itu = it0 + static_cast<uint32_t>(u - u0 + (pgi - pg)) * 2 * NSL;
                         uint32_t ks[NSL], vs[NSL];
@@ -839,80 +852,64 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             ks[j] = (itu + j) % MG_NS;
                             vs[j] = (itu + NSL + j) % MG_NS;
                         }
-                        const int self_t = (pgi == npg - 1) ? pos - pgi * MG_PAGE : -1;
                         unsigned long long tw0 = 0;
                         if (A.tl != nullptr && wtid == 0) tw0 = mg_now();
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((itu + j) / MG_NS) & 1, A.dbg, 6, p);
                         if (A.tl != nullptr && wtid == 0) wait_full_ns += mg_now() - tw0;
-                        // ---- scores of my 8 keys: 2 per iteration (one per half-warp), xor-reduce inside the half-warp
-                        float sc[4];
+                        // ---- score of my key: 32 dims per lane, reduce over the key's 4 lanes
+                        float dsum = 0.f;
+                        {
+                            const KVT* Kp = reinterpret_cast<const KVT*>(ring + ks[t_key / TPS] * MG_SLOT) + (t_key % TPS) * MG_HD + qc * 8;
 #pragma unroll
-                        for (int itq = 0; itq < 4; ++itq) {
-                            const int t = wq * 8 + itq * 2 + half;
-                            float kvv[8];
-                            const KVT* Kp = reinterpret_cast<const KVT*>(ring + ks[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + sub * 8;
-                            mg_load_kv<KVT, 8>(Kp, kvv);
-                            if (t == self_t) {
+                            for (int i = 0; i < 4; ++i) {
+                                float kvv[8];
+                                mg_load_kv<KVT, 8>(Kp + i * 32, kvv);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) kvv[i] = kself[i];
+                                for (int e2 = 0; e2 < 8; ++e2) dsum = fmaf(qv[i * 8 + e2], kvv[e2], dsum);
                             }
-                            float dsum = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) dsum = fmaf(qv[i], kvv[i], dsum);
-#pragma unroll
-                            for (int o = LPT / 2; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-                            sc[itq] = (pgi * MG_PAGE + t <= pos) ? dsum * A.scale : -INFINITY;
                         }
+                        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                        const float sc = (pgi * MG_PAGE + t_key < pos) ? dsum : -INFINITY;   // cached keys only: position `pos` is k_new
                         __syncwarp();
                         if (lane == 0) {
 #pragma unroll
                             for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[ks[j]]);       // one of the 8 warps' arrivals
                         }
-                        // ---- online softmax over my key slice
-                        float pm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+                        // ---- online softmax over my 8 keys (log2 domain)
+                        float pm = sc;
+                        pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 4));
+                        pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 8));
                         pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 16));
                         const float m_new = fmaxf(m_run, pm);
-                        float pr[4], corr = 1.f, psum = 0.f;
-                        if (m_new == -INFINITY) {                                   // every key of my slice masked so far
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) pr[i] = 0.f;
-                        } else {
-                            corr = expf(m_run - m_new);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                pr[i] = expf(sc[i] - m_new);
-                                psum += pr[i];
-                            }
+                        float pr = 0.f, corr = 1.f;
+                        if (m_new != -INFINITY) {                                   // else: every key of my slice masked so far
+                            corr = exp2f(m_run - m_new);
+                            pr = exp2f(sc - m_new);
                         }
+                        float psum = pr;                                            // the 4 lanes of a key hold the same pr
+                        psum += __shfl_xor_sync(0xffffffffu, psum, 4);
+                        psum += __shfl_xor_sync(0xffffffffu, psum, 8);
                         psum += __shfl_xor_sync(0xffffffffu, psum, 16);
                         l_run = l_run * corr + psum;
                         m_run = m_new;
 #pragma unroll
                         for (int i = 0; i < DPT; ++i) acc[i] *= corr;
-                        // ---- PV over my 8 keys
+                        // ---- PV over my 8 keys: lane owns 4 output dims
                         if (A.tl != nullptr && wtid == 0) tw0 = mg_now();
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((itu + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
                         if (A.tl != nullptr && wtid == 0) wait_full_ns += mg_now() - tw0;
 #pragma unroll
-                        for (int itq = 0; itq < 4; ++itq) {
-                            const float po = __shfl_xor_sync(0xffffffffu, pr[itq], 16);
-                            const float p0 = half == 0 ? pr[itq] : po, p1 = half == 0 ? po : pr[itq];
+                        for (int j = 0; j < 8; ++j) {
+                            const float pk = __shfl_sync(0xffffffffu, pr, 4 * j);
+                            const int t = wq * 8 + j;
+                            float vv[DPT];
+                            const KVT* Vp = reinterpret_cast<const KVT*>(ring + vs[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + lane * DPT;
+                            mg_load_kv<KVT, DPT>(Vp, vv);
 #pragma unroll
-                            for (int gk = 0; gk < 2; ++gk) {
-                                const int t = wq * 8 + itq * 2 + gk;
-                                float vv[DPT];
-                                const KVT* Vp = reinterpret_cast<const KVT*>(ring + vs[t / TPS] * MG_SLOT) + (t % TPS) * MG_HD + lane * DPT;
-                                mg_load_kv<KVT, DPT>(Vp, vv);
-                                if (t == self_t) {
-#pragma unroll
-                                    for (int i = 0; i < DPT; ++i) vv[i] = vself[i];
-                                }
-                                const float pk = gk == 0 ? p0 : p1;
-#pragma unroll
-                                for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pk, vv[i], acc[i]);
-                            }
+                            for (int i = 0; i < DPT; ++i) acc[i] = fmaf(pk, vv[i], acc[i]);
                         }
                         __syncwarp();
                         if (lane == 0) {
@@ -920,6 +917,25 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             for (int j = 0; j < NSL; ++j) mbar_arrive(&empty[vs[j]]);
                         }
                     }
+                    // ---- the current position: one extra key (k_new, v_new from this step's QKV epilogue), folded in by warp 0
+                    if (has_self && wq == 0) {
+                        const float4 q4 = *reinterpret_cast<const float4*>(q_sm + qbuf_sel * MG_HD + lane * DPT);
+                        float ss = q4.x * kself4.x;
+                        ss = fmaf(q4.y, kself4.y, ss);
+                        ss = fmaf(q4.z, kself4.z, ss);
+                        ss = fmaf(q4.w, kself4.w, ss);
+                        ss = warp_sum(ss);
+                        const float m_new = fmaxf(m_run, ss);
+                        const float corr = exp2f(m_run - m_new), ps = exp2f(ss - m_new);
+                        l_run = l_run * corr + ps;
+                        m_run = m_new;
+                        acc[0] = fmaf(ps, vself4.x, acc[0] * corr);
+                        acc[1] = fmaf(ps, vself4.y, acc[1] * corr);
+                        acc[2] = fmaf(ps, vself4.z, acc[2] * corr);
+                        acc[3] = fmaf(ps, vself4.w, acc[3] * corr);
+                    }
+                    if (un < u1 && wtid < MG_HD) q_sm[(qbuf_sel ^ 1) * MG_HD + wtid] = q_next * qscale;   // visible after the chunk's barriers
+                    qbuf_sel ^= 1;
                     // ---- chunk done: fold the 8 warp states in warp order -> chunk state ---------------------------------------
                     {
                         float* ps = st_sm + wq * MG_PSTR;
@@ -944,7 +960,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             const float mp = ps[MG_HD];
                             if (mp == -INFINITY) continue;                          // that warp's key slice was fully masked
                             const float Mn = fmaxf(M, mp);
-                            const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
+                            const float c1 = exp2f(M - Mn), c2 = exp2f(mp - Mn);
                             Ls = Ls * c1 + ps[MG_HD + 1] * c2;
                             O = O * c1 + ps[wtid] * c2;
                             M = Mn;
@@ -1004,7 +1020,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                                     op = cs_sm[j * MG_PSTR + wtid];
                                 }
                                 const float Mn = fmaxf(M, mp);
-                                const float c1 = expf(M - Mn), c2 = expf(mp - Mn);
+                                const float c1 = exp2f(M - Mn), c2 = exp2f(mp - Mn);
                                 Ls = Ls * c1 + lp * c2;
                                 O = O * c1 + op * c2;
                                 M = Mn;
