@@ -138,6 +138,7 @@ struct vcb_engine {
     float* mega_part = nullptr;
     unsigned int *mega_dbg_h = nullptr, *mega_dbg_d = nullptr;     // mapped pinned: readable after a device trap
     float *knew = nullptr, *vnew = nullptr, *mega_att_ws = nullptr;
+    __nv_bfloat16 *mact_d = nullptr, *mact_d2 = nullptr, *mact_f = nullptr, *mact_h = nullptr;   // tiled + swizzled B-operand images
     int* mega_att_cnt = nullptr;
     int64_t n_launches = 0;
     // profile mode: CUDA events around every launch, by kernel class
@@ -717,20 +718,20 @@ int mega_build(vcb_engine* e, int bpad) {
         ph.push_back(a);
         MegaPhase o = gemm(tm + 1, wp + 1, m.d, m.d, 0);
         o.ep.mode = EPI_RESID; o.ep.bias = Ly.b_out; o.ep.x = e->x_rows; o.ep.ld_out = m.d;
-        emit(o.ep, Ly.ln2_g, e->act_d2);
+        emit(o.ep, Ly.ln2_g, e->mact_d2);
         ph.push_back(o);
         MegaPhase f1 = gemm(tm + 2, wp + 2, m.F, m.d, 1);
-        f1.ep.mode = EPI_ACT; f1.ep.act = e->act_f; f1.ep.ld_out = m.F; f1.ep.act_kind = 1; f1.ep.bpad_out = bpad;
+        f1.ep.mode = EPI_ACT; f1.ep.act = e->mact_f; f1.ep.ld_out = m.F; f1.ep.act_kind = 1; f1.ep.bpad_out = bpad;
         fold(f1.ep, Ly.c_ff1, Ly.bp_ff1, dtiles);
         ph.push_back(f1);
         MegaPhase f2 = gemm(tm + 3, wp + 3, m.d, m.F, 2);
         f2.ep.mode = EPI_RESID; f2.ep.bias = Ly.b_ff2; f2.ep.x = e->x_rows; f2.ep.ld_out = m.d;
-        emit(f2.ep, l + 1 < m.L ? e->layers[l + 1].ln1_g : e->lnf_g, e->act_d);
+        emit(f2.ep, l + 1 < m.L ? e->layers[l + 1].ln1_g : e->lnf_g, e->mact_d);
         ph.push_back(f2);
     }
     const int KH = m.K * m.Hh;
     MegaPhase h1 = gemm(e->d_wmaps + 4 * m.L, e->d_wptrs + 4 * m.L, KH, m.d, 0);
-    h1.ep.mode = EPI_ACT; h1.ep.act = e->act_h; h1.ep.ld_out = KH; h1.ep.act_kind = 2; h1.ep.bpad_out = bpad;
+    h1.ep.mode = EPI_ACT; h1.ep.act = e->mact_h; h1.ep.ld_out = KH; h1.ep.act_kind = 2; h1.ep.bpad_out = bpad;
     fold(h1.ep, e->c_h1, e->bp_h1, dtiles);
     ph.push_back(h1);
     MegaPhase h2 = gemm(e->d_h2_maps, e->d_wptrs + 4 * m.L + 1, m.V, m.Hh, 3);
@@ -788,7 +789,9 @@ int mega_setup(vcb_engine* e) {
             dalloc(&e->vnew, static_cast<size_t>(R) * m.d) ||
             dalloc(&e->mega_att_ws, static_cast<size_t>(32) * m.H * e->max_pages_per_slot * 132) ||
             dalloc(&e->mega_att_cnt, static_cast<size_t>(32) * m.H) || dalloc(&e->d_wmaps, static_cast<size_t>(4) * m.L + 1) ||
-            dalloc(&e->d_wptrs, static_cast<size_t>(4) * m.L + 1 + m.K))
+            dalloc(&e->d_wptrs, static_cast<size_t>(4) * m.L + 1 + m.K) || dalloc(&e->mact_d, static_cast<size_t>(64) * m.d) ||
+            dalloc(&e->mact_d2, static_cast<size_t>(64) * m.d) || dalloc(&e->mact_f, static_cast<size_t>(64) * m.F) ||
+            dalloc(&e->mact_h, static_cast<size_t>(64) * m.K * m.Hh))
             return -1;
         VCB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->mega_dbg_h), 64, cudaHostAllocMapped));
         memset(e->mega_dbg_h, 0, 64);
@@ -830,10 +833,11 @@ int mega_step(vcb_engine* e, int n, cudaStream_t st) {
     const ModelDims& m = e->m;
     const int bpad = bpad_for(n), bi = bpad_idx(bpad);
     MegaArgs a;
-    a.tmB[0] = e->tm_act_d[bi];
-    a.tmB[1] = e->tm_act_d2[bi];
-    a.tmB[2] = e->tm_act_f[bi];
-    a.tmB[3] = e->tm_act_h[bi];
+    a.bbase[0] = e->mact_d;
+    a.bbase[1] = e->mact_d2;
+    a.bbase[2] = e->mact_f;
+    a.bbase[3] = e->mact_h;
+    (void)bi;
     a.ph = e->d_mega_ph[bpad == 32];
     a.nph = e->mega_nph;
     a.nvalid = n;
@@ -852,7 +856,7 @@ int mega_step(vcb_engine* e, int n, cudaStream_t st) {
     a.qbuf = e->qbuf;
     a.knew = e->knew;
     a.vnew = e->vnew;
-    a.att_out = e->act_d;
+    a.att_out = e->mact_d;
     a.att_ws = e->mega_att_ws;
     a.att_cnt = e->mega_att_cnt;
     a.row_pos = e->row_pos;
@@ -1106,7 +1110,7 @@ int vcb_destroy(vcb_engine* e) {
                     e->d_slots, e->tok_log, e->dbg_logits, e->st, e->gr, e->d_seqs};
     for (void* p : ptrs) cudaFree(p);
     void* mptrs[] = {e->d_mega_ph[0], e->d_mega_ph[1], e->d_wmaps, e->d_wptrs, e->mega_flags, e->mega_tile_cnt, e->mega_part, e->knew, e->vnew,
-                     e->mega_att_ws, e->mega_att_cnt, e->mega_tl};
+                     e->mega_att_ws, e->mega_att_cnt, e->mega_tl, e->mact_d, e->mact_d2, e->mact_f, e->mact_h};
     for (void* p : mptrs) cudaFree(p);
     if (e->mega_dbg_h) cudaFreeHost(e->mega_dbg_h);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1524,7 +1528,8 @@ int vcb_decode_step(vcb_engine* e, const int32_t* slots, int32_t n, const float*
                              fold ? e->layers[0].ln1_g : static_cast<const float*>(nullptr), e->act_d, bpad_for(n),
                              e->ln_stats, e->page_table, e->max_pages_per_slot, e->row_page, e->row_pages, e->row_forced,
                              e->mega_flags, e->mega_flags ? e->mega_nph : 0, reinterpret_cast<unsigned int*>(e->mega_tile_cnt),
-                             e->mega_flags ? e->mega_nph * e->mega_cnt_stride : 0));
+                             e->mega_flags ? e->mega_nph * e->mega_cnt_stride : 0,
+                             (fold && e->mega_grid > 0 && n <= 32) ? e->mact_d : static_cast<__nv_bfloat16*>(nullptr)));
     }
     LAUNCH_COUNT(e);
     e->cur_slot = e->row_slot;

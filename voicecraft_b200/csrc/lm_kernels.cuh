@@ -412,7 +412,8 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
                  const float* __restrict__ gamma0, __nv_bfloat16* __restrict__ act, int bpad, float* __restrict__ stats,
                  const int* __restrict__ page_table, int max_pages, int* __restrict__ row_page,
                  int* __restrict__ row_pages, int* __restrict__ row_forced, unsigned int* __restrict__ phase_flags,
-                 int n_phase_flags, unsigned int* __restrict__ tile_counters, int n_tile_counters) {
+                 int n_phase_flags, unsigned int* __restrict__ tile_counters, int n_tile_counters,
+                 __nv_bfloat16* __restrict__ act_tiled) {
     __shared__ float red[8];
     pdl_launch_dependents();
     pdl_wait();
@@ -451,6 +452,12 @@ step_prep_kernel(const int* __restrict__ slots, int n, SlotState* __restrict__ s
             split_bf16(gamma0[c] * v, hi, lo);
             act[static_cast<size_t>(r) * d + c] = hi;
             act[static_cast<size_t>(r + bpad) * d + c] = lo;
+            if (act_tiled) {       // persistent step kernel: the same operand as the pre-swizzled image of its UMMA tiles (mega_step.cu)
+                const int kk = c & 63, rows2 = 2 * bpad;
+                const size_t t0 = static_cast<size_t>(c >> 6) * rows2;
+                act_tiled[(t0 + r) * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7))] = hi;
+                act_tiled[(t0 + r + bpad) * 64 + ((((kk >> 3) ^ ((r + bpad) & 7)) << 3) | (kk & 7))] = lo;
+            }
             s1 += v;
             s2 += v * v;
         }

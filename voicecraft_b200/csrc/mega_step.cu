@@ -175,6 +175,13 @@ __device__ __forceinline__ uint2 mg_pack_bf16x4(float a, float b, float c, float
     return r;
 }
 __device__ __forceinline__ float mg_bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// Element offset of activation (k, row) in the tiled + pre-swizzled B-operand image (MegaArgs::bbase): k-block k/64 is one
+// contiguous tile of rows2 = 2*bpad rows x 128 bytes; inside a row the 16-byte chunk (k%64)/8 is XORed with row % 8, which is
+// exactly where TMA's SWIZZLE_128B would have put it in shared memory (rows2 is a multiple of 8).
+__device__ __forceinline__ size_t mg_act_off(int k, int row, int rows2) {
+    const int kk = k & 63;
+    return (static_cast<size_t>(k >> 6) * rows2 + row) * 64 + ((((kk >> 3) ^ (row & 7)) << 3) | (kk & 7));
+}
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Split-K hand-over of one output tile, reduce-scatter through L2: every CTA that contributed a partial of the tile
@@ -325,8 +332,8 @@ __device__ __forceinline__ void mg_epi_finish(const MegaArgs& A, const MegaPhase
                         hi[i] = mg_bf16_round(v);
                         lo[i] = v - hi[i];
                     }
-                    __stcg(reinterpret_cast<uint2*>(ep.act + static_cast<size_t>(row) * ep.ld_out + m0), mg_pack_bf16x4(hi[0], hi[1], hi[2], hi[3]));
-                    __stcg(reinterpret_cast<uint2*>(ep.act + static_cast<size_t>(row + ep.bpad_out) * ep.ld_out + m0),
+                    __stcg(reinterpret_cast<uint2*>(ep.act + mg_act_off(m0, row, 2 * ep.bpad_out)), mg_pack_bf16x4(hi[0], hi[1], hi[2], hi[3]));
+                    __stcg(reinterpret_cast<uint2*>(ep.act + mg_act_off(m0, row + ep.bpad_out, 2 * ep.bpad_out)),
                            mg_pack_bf16x4(lo[0], lo[1], lo[2], lo[3]));
                     break;
                 }
@@ -356,8 +363,8 @@ __device__ __forceinline__ void mg_epi_finish(const MegaArgs& A, const MegaPhase
                     p1 += xn[i];
                     p2 += xn[i] * xn[i];
                 }
-                __stcg(reinterpret_cast<uint2*>(ep.next_act + static_cast<size_t>(row) * ep.next_ld + m0), mg_pack_bf16x4(hi[0], hi[1], hi[2], hi[3]));
-                __stcg(reinterpret_cast<uint2*>(ep.next_act + static_cast<size_t>(row + ep.next_bpad) * ep.next_ld + m0),
+                __stcg(reinterpret_cast<uint2*>(ep.next_act + mg_act_off(m0, row, 2 * ep.next_bpad)), mg_pack_bf16x4(hi[0], hi[1], hi[2], hi[3]));
+                __stcg(reinterpret_cast<uint2*>(ep.next_act + mg_act_off(m0, row + ep.next_bpad, 2 * ep.next_bpad)),
                        mg_pack_bf16x4(lo[0], lo[1], lo[2], lo[3]));
             }
             p1 = warp_sum(p1);
@@ -617,7 +624,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     const int bs = bit % MG_NB;
                     if (bit >= MG_NB) mg_wait(&bempty[bs], ((bit / MG_NB) - 1) & 1, A.dbg, 3, p);
                     mbar_arrive_expect_tx(&bfull[bs], B_BYTES);
-                    tma_load_2d(bring + bs * MG_BSLOT, &A.tmB[P.b_map], &bfull[bs], P.b_col_off + g * P.b_grp_stride + kbi * 64, 0);
+                    const int kglob = (P.b_col_off + g * P.b_grp_stride) / 64 + kbi;            // k-block inside the operand's buffer
+                    tma_bulk_g2s(bring + bs * MG_BSLOT, A.bbase[P.b_map] + static_cast<size_t>(kglob) * BN * 64, B_BYTES, &bfull[bs]);
                 }
                 mg_tl(A, p, 4);
             }
@@ -969,8 +977,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             const float o = O / Ls;
                             __nv_bfloat16 hi, lo;
                             split_bf16(o, hi, lo);
-                            A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                            A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                            A.att_out[mg_act_off(static_cast<int>(ocol) + wtid, r, 2 * A.bpad)] = hi;
+                            A.att_out[mg_act_off(static_cast<int>(ocol) + wtid, r + A.bpad, 2 * A.bpad)] = lo;
                         } else if (!spans) {                                        // all chunks of the item are mine: keep it on chip
                             cs_sm[cidx * MG_PSTR + wtid] = O;
                             if (wtid == 0) {
@@ -1028,8 +1036,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             const float o = O / Ls;
                             __nv_bfloat16 hi, lo;
                             split_bf16(o, hi, lo);
-                            A.att_out[static_cast<size_t>(r) * A.d + ocol + wtid] = hi;
-                            A.att_out[static_cast<size_t>(r + A.bpad) * A.d + ocol + wtid] = lo;
+                            A.att_out[mg_act_off(static_cast<int>(ocol) + wtid, r, 2 * A.bpad)] = hi;
+                            A.att_out[mg_act_off(static_cast<int>(ocol) + wtid, r + A.bpad, 2 * A.bpad)] = lo;
                         }
                         if (spans && do_fold && wtid == 0) A.att_cnt[rh] = 0;
                     }

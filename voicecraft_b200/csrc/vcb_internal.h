@@ -76,7 +76,7 @@ struct MegaPhase {
     int type = MEGA_GEMM;
     // GEMM: `groups` matrices of tiles_per_group x kb 16 KB weight blocks (groups > 1: the K second-stage logit heads)
     int groups = 1, tiles_per_group = 0, kb = 0, Nout = 0;
-    int b_map = 0, b_col_off = 0, b_grp_stride = 0, col_grp_stride = 0;
+    int b_map = 0, b_col_off = 0, b_grp_stride = 0, col_grp_stride = 0;   // b_col_off / b_grp_stride in elements (multiples of 64)
     const CUtensorMap* tmA = nullptr;         // device array [groups]
     const void* const* wptr = nullptr;        // device array [groups]: packed weights (contiguous 16 KB blocks), L2 prefetch
     const float* const* grp_bias = nullptr;   // device array [groups] or null (ep.bias)
@@ -88,7 +88,11 @@ struct MegaPhase {
     int done_target = 0;                      // completions that finish this phase (tiles, or CTAs for ATTN)
 };
 struct MegaArgs {
-    CUtensorMap tmB[4];                 // activation operands: 0 act_d, 1 act_d2, 2 act_f, 3 act_h
+    // Activation (B) operands: 0 act_d, 1 act_d2, 2 act_f, 3 act_h, each stored as the shared-memory IMAGE of its UMMA tiles:
+    // [K/64 k-blocks][2*bpad rows (hi rows, then lo rows)][64] bf16 with the 128-byte swizzle already applied (16-byte chunk c
+    // of row r sits at chunk c ^ (r & 7)), so a tile is one contiguous 2*bpad*128-byte bulk copy -- no tensor map, no 64
+    // scattered 128-byte rows per tile (see mg_act_off in mega_step.cu).
+    const __nv_bfloat16* bbase[4] = {nullptr, nullptr, nullptr, nullptr};
     const MegaPhase* ph = nullptr;      // device array
     int nph = 0, nvalid = 0, bpad = 0, kv_fp32 = 0;
     int ns = 11, nb = 6;                // ring depths: ns * 16 KB + nb * 8 KB <= 224 KB
