@@ -1,6 +1,6 @@
 """Per-phase device timeline of the persistent decode-step kernel at the bench shape (830M, B=32), over ALL CTAs.
 Events per (cta, phase): 0 dep (B producer saw the previous phase complete), 1 acc (first accumulator of the phase ready),
-2 epi (this CTA finished a tile epilogue as last arriver), 3 end (this CTA's last segment handed over), 7 ring producer issued
+2 epi (this CTA finished its share of a tile's rows: reduce + epilogue + count), 8 all contributors of the tile have arrived, 3 end (this CTA's last segment handed over), 7 ring producer issued
 the phase's last item; GEMM phases: 4 B producer issued its last activation tile, 5 first MMA issued, 6 last MMA issued;
 attention phases: 4 dependency seen, 5 loop end, 6 flag published.
 usage: python scripts/mega_timeline.py [steps_before] [kv]"""
@@ -42,8 +42,7 @@ for p in range(nph.value):
     if nm == "attn":
         print(f"{p:3d} {nm:5s} dep {f(t[:, p, 4])}  loop_end {f(t[:, p, 5])}  flag {f(t[:, p, 6])}  prod {f(t[:, p, 7])}  | waits: workers on data {f(dur[:, p, 0])}  producer on free slots {f(dur[:, p, 1])}  on flight cap {f(dur[:, p, 2])}")
     else:
-        ep = t[:, p, 8:12] - t[:, p, 8:9]
-        print(f"        last-arriver path (us after arrival): operands {f(ep[:, 1])}  partials summed {f(ep[:, 2])}  stores issued {f(ep[:, 3])}  flag {f(t[:, p, 2] - t[:, p, 8])}")
+        print(f"        hand-over (us): first accumulator -> all contributors of the tile arrived {f(t[:, p, 8] - t[:, p, 1])}   -> my rows reduced, epilogue done, counted {f(t[:, p, 2] - t[:, p, 8])}")
         print(f"{p:3d} {nm:5s} dep {f(t[:, p, 0])}  mma0 {f(t[:, p, 5])}  Blast {f(t[:, p, 4])}  mmaN {f(t[:, p, 6])}  acc {f(t[:, p, 1])}  end {f(t[:, p, 3])}  epi {f(t[:, p, 2])}  prod {f(t[:, p, 7])}")
 print("kernel span: %.1f us" % np.nanmax(t))
 # per-layer summary over the middle layers

@@ -478,17 +478,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
             const uint64_t pol = l2_policy_evict_first();
             uint32_t it = 0, landed = 0;
             const uint32_t flight = static_cast<uint32_t>(A.flight);
-            unsigned long long wait_empty_ns = 0, wait_flight_ns = 0;
             auto acquire = [&](int p) -> int {
                 const int s = it % MG_NS;
-                unsigned long long tw0 = 0;
-                if (A.tl != nullptr) tw0 = mg_now();
                 if (it >= MG_NS) mg_wait(&empty[s], ((it / MG_NS) - 1) & 1, A.dbg, 0, p);
-                if (A.tl != nullptr) {
-                    const unsigned long long t1 = mg_now();
-                    wait_empty_ns += t1 - tw0;
-                    tw0 = t1;
-                }
                 // Bound the loads IN FLIGHT (issued, not landed), not just the ring's capacity: this SM's memory pipe serves
                 // requests roughly in order, so the activation tiles / partials a phase hand-over is waiting for queue behind
                 // whatever the ring still has outstanding (11 x 16 KB at this SM's ~44 GB/s HBM share = 4 us of backlog;
@@ -498,7 +490,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     mg_wait(&full[landed % MG_NS], (landed / MG_NS) & 1, A.dbg, 9, p);
                     ++landed;
                 }
-                if (A.tl != nullptr) wait_flight_ns += mg_now() - tw0;
                 ++it;
                 *s_prod = it;
                 return s;
@@ -552,11 +543,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     }
                 }
                 mg_tl(A, p, 7);
-                if (A.tl != nullptr) {
-                    A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + 13] = wait_empty_ns + 1;
-                    A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + 14] = wait_flight_ns + 1;
-                    wait_empty_ns = wait_flight_ns = 0;
-                }
             }
         }
     } else if (warp == 1) {
@@ -747,37 +733,45 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                     float* pdst = A.part + (static_cast<size_t>(cta) * MEGA_MAXSEG + (tile - first_tile)) * BPAD * 128 + ml;
 #pragma unroll
                     for (int j = 0; j < HB; ++j) __stcg(pdst + (grp * HB + j) * 128, v[j]);
-                    // hand-over: publish my partial (the block barrier orders every worker's stores before thread 0's GPU-scope
-                    // fence -- fences are cumulative), count in, fetch my rows' epilogue operands WHILE the other contributors
-                    // arrive, then reduce + epilogue my share of the tile's rows
+                    // publish my partial: the block barrier orders every worker's stores before thread 0's GPU-scope fence
+                    // (fences are cumulative), then count in.  ALL my partials of the phase go out before I wait for anybody:
+                    // waiting per tile would chain the tiles (tile t+1's partial stuck behind the wait for tile t's last
+                    // contributor -- measured as a 48-tile domino, 60 us per phase).
                     mg_bar_workers();
-                    const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, Ge);
-                    const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, Ge);
-                    const int ncontrib = c_last - c_first + 1;
-                    const int sidx = cta - c_first;
-                    const int row_begin = sidx * BPAD / ncontrib, row_end = (sidx + 1) * BPAD / ncontrib;
-                    int* cnt = A.tile_cnt + p * A.tile_cnt_stride + tile;
                     if (wtid == 0) {
                         __threadfence();
-                        atomicAdd(cnt, 1);
+                        atomicAdd(A.tile_cnt + p * A.tile_cnt_stride + tile, 1);
                     }
+                }
+                if (wtid == 0) mg_tl(A, p, 3);
+                // ---- second pass: my share of every tile I contributed to ----------------------------------------------------
+                if (b0 < b1) {
                     const GemmEpilogue ep = P.ep;           // by value: no re-loads of its fields between the epilogue's stores
-                    MgEpiRegs<BPAD> R;
-                    mg_epi_prefetch<BPAD>(A, P, ep, tile, row_begin, row_end, wq, lane, R);
-                    if (wtid == 0) {
-                        mg_wait_flag(reinterpret_cast<const unsigned int*>(cnt), static_cast<unsigned int>(ncontrib), A.dbg, 10, p);
-                        mg_tl(A, p, 8);
+                    const int last_tile = (b1 - 1) / P.kb;
+                    for (int tile = first_tile; tile <= last_tile; ++tile) {
+                        const int c_first = mg_owner(static_cast<long long>(tile) * P.kb, T, Ge);
+                        const int c_last = mg_owner(static_cast<long long>(tile + 1) * P.kb - 1, T, Ge);
+                        const int ncontrib = c_last - c_first + 1;
+                        const int sidx = cta - c_first;
+                        const int row_begin = sidx * BPAD / ncontrib, row_end = (sidx + 1) * BPAD / ncontrib;
+                        // operands that do not depend on the other contributors are fetched WHILE they arrive
+                        MgEpiRegs<BPAD> R;
+                        mg_epi_prefetch<BPAD>(A, P, ep, tile, row_begin, row_end, wq, lane, R);
+                        if (wtid == 0) {
+                            mg_wait_flag(reinterpret_cast<const unsigned int*>(A.tile_cnt + p * A.tile_cnt_stride + tile),
+                                         static_cast<unsigned int>(ncontrib), A.dbg, 10, p);
+                            mg_tl(A, p, 8);
+                        }
+                        mg_bar_workers();
+                        mg_epi_finish<BPAD>(A, P, ep, p, tile, c_first, ncontrib, T, Ge, row_begin, row_end, wq, lane, R);
+                        mg_bar_workers();
+                        if (wtid == 0) {
+                            __threadfence();
+                            mg_fence_proxy_async();
+                            atomicAdd(A.flags + p, 1u);
+                            mg_tl(A, p, 2);
+                        }
                     }
-                    mg_bar_workers();
-                    mg_epi_finish<BPAD>(A, P, ep, p, tile, c_first, ncontrib, T, Ge, row_begin, row_end, wq, lane, R);
-                    mg_bar_workers();
-                    if (wtid == 0) {
-                        __threadfence();
-                        mg_fence_proxy_async();
-                        atomicAdd(A.flags + p, 1u);
-                        mg_tl(A, p, 2);
-                    }
-                    if (wtid == 0) mg_tl(A, p, 3);
                 }
             } else {
                 // ===== attention: units [u0, u1), cut at chunk boundaries ======================================================
@@ -804,7 +798,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 if (wtid == 0) mg_tl(A, p, 4);
                 const int kj = lane >> 2, qc = lane & 3;                             // my key inside the warp's slice, my dim quarter
                 const uint32_t it0 = it;
-                unsigned long long wait_full_ns = 0;
                 const float qscale = A.scale * 1.4426950408889634f;
                 int qbuf_sel = 0;
                 if (u0 < u1 && wtid < MG_HD) {                                        // first chunk's q (exposed once per phase)
@@ -860,11 +853,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                             ks[j] = (itu + j) % MG_NS;
                             vs[j] = (itu + NSL + j) % MG_NS;
                         }
-                        unsigned long long tw0 = 0;
-                        if (A.tl != nullptr && wtid == 0) tw0 = mg_now();
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[ks[j]], ((itu + j) / MG_NS) & 1, A.dbg, 6, p);
-                        if (A.tl != nullptr && wtid == 0) wait_full_ns += mg_now() - tw0;
                         // ---- score of my key: 32 dims per lane, reduce over the key's 4 lanes
                         float dsum = 0.f;
                         {
@@ -905,10 +895,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
 #pragma unroll
                         for (int i = 0; i < DPT; ++i) acc[i] *= corr;
                         // ---- PV over my 8 keys: lane owns 4 output dims
-                        if (A.tl != nullptr && wtid == 0) tw0 = mg_now();
 #pragma unroll
                         for (int j = 0; j < NSL; ++j) mg_wait(&full[vs[j]], ((itu + NSL + j) / MG_NS) & 1, A.dbg, 7, p);
-                        if (A.tl != nullptr && wtid == 0) wait_full_ns += mg_now() - tw0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float pk = __shfl_sync(0xffffffffu, pr, 4 * j);
@@ -1047,7 +1035,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mega_step_kernel(const __grid_c
                 it = it0 + static_cast<uint32_t>(u1 - u0) * 2 * NSL;
                 // this CTA's share of the phase is done (merged outputs are counted by whoever merged them)
                 if (wtid == 0) mg_tl(A, p, 5);
-                if (A.tl != nullptr && wtid == 0) A.tl[(static_cast<size_t>(blockIdx.x) * A.nph + p) * 16 + 12] = wait_full_ns + 1;
                 __threadfence();
                 mg_bar_workers();
                 if (wtid == 0) {
