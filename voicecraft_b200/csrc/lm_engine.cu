@@ -127,7 +127,7 @@ struct vcb_engine {
     int* cur_att_cnt = nullptr;
     __nv_bfloat16* cur_act_d = nullptr;
     // persistent decode-step kernel (mega_step.cu): phase tables per bpad (16 / 32), flags, split-K workspace
-    int opt_mega = 1, mega_grid = 0, mega_nph = 0, mega_cnt_stride = 0;
+    int opt_mega = 0, mega_grid = 0, mega_nph = 0, mega_cnt_stride = 0;      // VCB_MEGA=1: decode steps through the persistent kernel
     MegaPhase* d_mega_ph[2] = {nullptr, nullptr};
     CUtensorMap* d_wmaps = nullptr;        // device copies of the weight tensor maps: [L][qkv, out, ff1, ff2], h1
     const void** d_wptrs = nullptr;        // raw packed-weight pointers, same order, then the K second-stage head matrices
