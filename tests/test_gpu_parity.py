@@ -186,9 +186,9 @@ def test_generator_stream_matches_torch_multinomial_on_device():
     assert torch.equal(after, torch.empty(4, device="cuda").exponential_(1))
 
 
-def test_chain_path_bpad32_matches_oracle():
-    """Best-of-20 on the 512-d model: 20 rows -> Bpad 32, i.e. the persistent GEMM-chain kernel with 4 rows per CTA
-    (the fixtures only reach Bpad 16).  Oracle with the same rounding policy and the same noise."""
+def test_bpad32_best_of_20_matches_oracle():
+    """Best-of-20 on the 512-d model: 20 rows -> Bpad 32 (UMMA N = 64; the fixtures only reach Bpad 16).  Oracle with the
+    same rounding policy and the same noise."""
     from oracle import lm_oracle
     from voicecraft_b200 import synthetic
     cfg = synthetic.make_config("small")
@@ -333,16 +333,6 @@ def test_wide_prefill_bf16_kv_matches_oracle(monkeypatch):
     assert np.array_equal(res.cpu().numpy(), ores.numpy())
 
 
-@pytest.mark.skipif(os.environ.get("VCB_TEST_EXPERIMENTAL") != "1",
-                    reason="grouped prefill attention (csrc/prefill_attn.cuh) has not been run on hardware yet; "
-                           "VCB_TEST_EXPERIMENTAL=1 enables its bring-up tests")
-@pytest.mark.parametrize("name", ["tts_topk40", "batch3", "edit2", "tts_small"])
-def test_experimental_grouped_prefill_attention(name, monkeypatch):
-    monkeypatch.setenv("VCB_PREFILL_WIDE", "1")
-    monkeypatch.setenv("VCB_PREFILL_ATT_GROUP", "4")
-    res, trace, g = _run_case(name, CASES[name], "fp32")
-    assert np.array_equal(res.cpu().numpy(), g["res"]), "token ids differ from the reference fixture"
-
 
 # ==========================================================================================================================
 # Headline shape (BASELINE.json configs[1]): giga830M, B = 32 independent utterances, K = 4, top-k 40 sampling, one random
@@ -477,3 +467,30 @@ def test_continuous_batching_equals_single_calls():
     assert cb.stats["prefills"] >= 3 and cb.stats["max_active"] == 4
     for i, (a, (b, _)) in enumerate(zip(singles, out)):
         assert torch.equal(a, b), f"utterance {i}"
+
+
+# ==========================================================================================================================
+# The persistent decode-step kernel (csrc/mega_step.cu, opt-in: VCB_MEGA=1) against the same fixtures / oracle.
+# ==========================================================================================================================
+@pytest.mark.parametrize("name", ["tts_topk40", "tts_small", "batch3", "batch2_k8", "edit2", "edit3_noeos"])
+def test_persistent_kernel_matches_reference_fixture(name, monkeypatch):
+    monkeypatch.setenv("VCB_MEGA", "1")
+    res, trace, g = _run_case(name, CASES[name], "fp32")
+    for step, ref in zip(g["trace_steps"], g["trace_logits"]):
+        got = trace[int(step)].cpu().numpy()
+        live = ref > -9999
+        diff = np.abs(got - ref)[live]
+        assert int((diff > LOGIT_TOL).sum()) <= 1, f"step {step}: max {diff.max()}"
+    assert np.array_equal(res.cpu().numpy(), g["res"]), "token ids differ from the reference fixture"
+
+
+@pytest.mark.parametrize("kv", ["fp32", "bf16"])
+def test_persistent_kernel_headline_830M_b32(kv, monkeypatch):
+    """Same requirement as test_headline_830M_b32_matches_oracle, decode steps through the persistent kernel."""
+    monkeypatch.setenv("VCB_MEGA", "1")
+    test_headline_830M_b32_matches_oracle(kv)
+
+
+def test_persistent_kernel_rows_do_not_depend_on_the_batch(monkeypatch):
+    monkeypatch.setenv("VCB_MEGA", "1")
+    test_per_utterance_streams_batch_rows_equal_single_calls()

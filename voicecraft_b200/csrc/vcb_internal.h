@@ -49,23 +49,6 @@ struct GemmEpilogue {
 };
 static constexpr int STATS_ROWS = 128;
 
-// Persistent GEMM chain (gemm_chain.cu): up to CHAIN_MAXP dependent GEMMs in one launch.
-static constexpr int CHAIN_MAXP = 8;
-struct ChainPhase {
-    CUtensorMap tmA;                    // pre-tiled weights of this phase
-    GemmEpilogue ep;
-    int Nout = 0, total_kb = 0, b_map = 0, b_col_off = 0;
-};
-struct ChainArgs {
-    CUtensorMap tmB[4];                 // activation operands: 0 act_d, 1 act_d2, 2 act_f, 3 act_h
-    ChainPhase ph[CHAIN_MAXP];
-    int nphases = 0, nvalid = 0;
-    unsigned int* ctr = nullptr;        // device-wide barrier counter (monotonic)
-    unsigned int epoch = 0;             // counter value before this launch's first arrival
-};
-int chain_launch(const ChainArgs& args, int bpad, int nclusters, int pdl, cudaStream_t st);
-int chain_max_clusters(int bpad);
-
 // ---------------------------------------------------------------------------------------------------
 // Persistent decode-step kernel (mega_step.cu): one launch runs every layer of a decode step.
 // ---------------------------------------------------------------------------------------------------
