@@ -44,7 +44,11 @@ int enc_decode(enc_engine* e, const int64_t* codes_dev, float* wav_dev, int32_t 
  * ResidualVectorQuantizer.encode).  Needs the "enc.*" weights: "enc.conv_in.weight", "enc.down{i}.res{j}.conv1.weight",
  * "enc.down{i}.conv.weight" (strided), "enc.lstm.*", "enc.conv_out.weight". */
 int enc_encode(enc_engine* e, const float* wav_dev, int64_t* codes_dev, int32_t B, int32_t N, void* stream);
-int64_t enc_counter(enc_engine* e, const char* name); /* "launches", "hop", "flops_per_frame" */
+int64_t enc_counter(enc_engine* e, const char* name); /* "launches", "hop", "flops_per_frame", "tc_enabled", "tc_decodes" */
+/* Debug / tests: an intermediate tensor of the last enc_decode on the tensor-core path ("z", "x0", "u0", "x1.raw", "x1.elu",
+ * "h1.0", "o1.0", ...), reassembled from its bf16 (hi, lo) planes as fp32 [B][C][halo + T] on the host.  dims = {B, C, halo + T,
+ * halo}; host_out == NULL only queries dims. */
+int enc_debug_tensor(enc_engine* e, const char* name, float* host_out, int64_t cap, int32_t* dims);
 
 #ifdef __cplusplus
 }

@@ -23,4 +23,4 @@ ms = e0.elapsed_time(e1) / n
 fl = _lib.load().enc_counter(tok._engine(), b"flops_per_frame") * B * T
 print(json.dumps({"workload": f"EnCodec SEANet decode B={B} x {T} frames (K=4, 16 kHz)", "ms": ms, "utt_per_s": B / ms * 1e3,
                   "audio_s_per_s": B * T / 50 / ms * 1e3, "codec_tokens_per_s": B * T * 4 / ms * 1e3,
-                  "tflops_fp32": fl / ms / 1e9, "flops": fl, "kernels": "fp32 CUDA-core implicit GEMM (round 1)"}))
+                  "tflops_fp32": fl / ms / 1e9, "flops": fl, "tc_path": bool(_lib.load().enc_counter(tok._engine(), b"tc_enabled"))}))

@@ -136,3 +136,57 @@ def test_cuda_encode_decode_round_trip_full_size():
     assert not (bad & (bad.cumsum(dim=1) == 1) & (gaps >= 1e-4)).any(), f"{int(bad.sum())} codes differ"
     out = tok.decode_codes(codes)
     assert out.shape == (2, 1, 16000)
+
+
+def _counter(tok, name):
+    from voicecraft_b200 import _lib
+    return int(_lib.load().enc_counter(tok._engine(), name.encode()))
+
+
+@pytest.mark.gpu
+def test_tensor_core_decoder_runs_the_default_codec():
+    """The default 16 kHz codec must decode on the tcgen05 path (csrc/codec_tc.cu), not fall back to the CUDA-core kernels.
+    Tolerance (stated for the 3-pass bf16 hi/lo product, fp32 accumulation): waveform SNR >= 80 dB against the fp32 oracle
+    and max |err| <= 2e-4 of the peak."""
+    cfg = eo.default_config()
+    sd = eo.make_state_dict(cfg, seed=7)
+    codes = torch.randint(0, 2048, (3, 4, 61), generator=torch.Generator().manual_seed(15))
+    ref = eo.decode(cfg, sd, codes)
+    tok = _gpu_tok(cfg, sd)
+    wav = tok.decode_codes(codes.cuda()).cpu()
+    assert _counter(tok, "tc_enabled") == 1 and _counter(tok, "tc_decodes") == 1
+    snr = 10 * torch.log10((ref ** 2).sum() / ((wav - ref) ** 2).sum()).item()
+    assert snr >= 80.0, snr
+    assert (wav - ref).abs().max() <= 2e-4 * max(1.0, ref.abs().max().item())
+    # shorter than the reflect paddings need: the CUDA-core kernels take over, same answer
+    short = tok.decode_codes(codes[:, :, :5].cuda()).cpu()
+    assert _counter(tok, "tc_decodes") == 1
+    assert (short - eo.decode(cfg, sd, codes[:, :, :5])).abs().max() < 5e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["small_causal_reflect", "small_constpad", "mid_default"])
+def test_cuda_core_decoder_matches_fixture(name, golden_dir, monkeypatch):
+    """VCB_CODEC_TC=0 keeps the round-1 fp32 CUDA-core decoder reachable (it still serves the configurations the tensor-core
+    path does not cover); same fixtures, same tolerance."""
+    monkeypatch.setenv("VCB_CODEC_TC", "0")
+    g = np.load(os.path.join(golden_dir, "codec.npz"))
+    over, seed = CASES[name]
+    cfg = eo.default_config(**over)
+    tok = _gpu_tok(cfg, eo.make_state_dict(cfg, seed=seed))
+    wav = tok.decode_codes(torch.from_numpy(g[f"{name}.codes"]).cuda()).cpu().numpy()
+    assert _counter(tok, "tc_enabled") == 0
+    assert np.abs(wav - g[f"{name}.wav"]).max() < 2e-4
+
+
+@pytest.mark.gpu
+def test_tensor_core_decoder_chunking_is_invisible(monkeypatch):
+    """A workspace limit that forces the batch through several chunks must not change a bit of the waveform."""
+    cfg = eo.default_config(n_filters=16, dimension=64, bins=256)
+    sd = eo.make_state_dict(cfg, seed=9)
+    codes = torch.randint(0, 256, (11, 4, 33), generator=torch.Generator().manual_seed(6)).cuda()
+    full = _gpu_tok(cfg, sd).decode_codes(codes)
+    monkeypatch.setenv("VCB_CODEC_WS_GB", "0.02")
+    tok = _gpu_tok(cfg, sd)
+    assert torch.equal(tok.decode_codes(codes), full)
+    assert _counter(tok, "tc_decodes") == 1

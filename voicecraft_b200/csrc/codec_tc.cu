@@ -37,7 +37,7 @@ namespace vcb {
 
 static constexpr int TC_BM = 128;
 static constexpr int TC_BK = 64;
-static constexpr int TC_EPI_WARPS = 8;
+static constexpr int TC_EPI_WARPS = 16;
 static constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 static constexpr int TC_MAX_KB = 64;
 enum { TC_MODE_CONV = 0, TC_MODE_LSTM = 1 };
@@ -49,7 +49,7 @@ struct TcTap {
 };
 
 struct TcCall {
-    int total_kb, ntiles, rows_total, row_base;
+    int total_kb, ntiles, mtiles, rows_total, row_base;
     int rcap[2];                       // rows per plane of A source 0 / 1 (lo plane = + rcap rows)
     int in_div, in_tm, in_halo, T_in, B;   // A row -> (b, t): utterance-major (row / Tp, row % Tp - halo) or time-major
     int mode, up, Cout, Nstore;        // GEMM column n -> (phase p = n / Cout, channel n % Cout); columns >= Nstore are padding
@@ -77,34 +77,35 @@ struct TcSmem {
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
 };
 
-__device__ __forceinline__ float tc_elu(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU for the planes the next layer reads: exp through ex2.approx (absolute error ~2e-7, far below the 2^-17 relative
+// error of the hi/lo split it feeds)
+__device__ __forceinline__ float tc_elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 __device__ __forceinline__ float tc_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
-// 8 fp32 -> 8 bf16 hi + 8 bf16 lo
+// two fp32 -> packed bf16x2 hi parts and bf16x2 lo parts (same roundings as split_bf16)
+__device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
 __device__ __forceinline__ void tc_split8(const float* v, uint4& hi, uint4& lo) {
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * u], h0, l0);
-        split_bf16(v[2 * u + 1], h1, l1);
-        __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
-        hw[u] = *reinterpret_cast<uint32_t*>(&hh);
-        lw[u] = *reinterpret_cast<uint32_t*>(&ll);
-    }
-    hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    tc_split2(v[0], v[1], hi.x, lo.x);
+    tc_split2(v[2], v[3], hi.y, lo.y);
+    tc_split2(v[4], v[5], hi.z, lo.z);
+    tc_split2(v[6], v[7], hi.w, lo.w);
 }
 
-// 32 consecutive channels of one row -> both planes (and the mirrored halo row, if any)
+// CW consecutive channels of one row -> both planes (and the mirrored halo row, if any)
+template <int CW>
 __device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long plane, int ld, long long row, long long mirror,
-                                                int co0, const float (&v)[32], bool elu, bool zero_mirror) {
-    uint4 hi[4], lo[4];
+                                                int co0, const float (&v)[CW], bool elu, bool zero_mirror) {
+    uint4 hi[CW / 8], lo[CW / 8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < CW / 8; ++j) {
         float w[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) w[u] = elu ? tc_elu(v[8 * j + u]) : v[8 * j + u];
@@ -113,7 +114,7 @@ __device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long p
     uint4* ph = reinterpret_cast<uint4*>(base + row * ld + co0);
     uint4* pl = reinterpret_cast<uint4*>(base + plane + row * ld + co0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < CW / 8; ++j) {
         ph[j] = hi[j];
         pl[j] = lo[j];
     }
@@ -122,79 +123,100 @@ __device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long p
         uint4* ml = reinterpret_cast<uint4*>(base + plane + mirror * ld + co0);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CW / 8; ++j) {
             mh[j] = zero_mirror ? z : hi[j];
             ml[j] = zero_mirror ? z : lo[j];
         }
     }
 }
 
-__device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, int n0, float (&v)[32]) {
+template <int CW>
+__device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, int n0, float (&v)[CW]) {
     const int p = n0 / c.Cout, co0 = n0 - p * c.Cout;
     const int t_out = t * c.up + p;
+    {
+        const float4* b4 = reinterpret_cast<const float4*>(c.bias + n0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += c.bias[n0 + j];
+        for (int j = 0; j < CW / 4; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+    }
     if (c.f32 != nullptr) {
         float* dst = c.f32 + (b * c.f_sb + t_out * c.f_st + c.f_off) * c.f_ld + co0;
         if (c.f_scalar) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CW; ++j)
                 if (co0 + j < c.f_valid) dst[j] = v[j];
         } else if (co0 < c.f_valid) {
             float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CW / 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
     }
     if (c.raw != nullptr || c.elu != nullptr) {
         const long long row = b * c.o_sb + t_out * c.o_st + c.o_off;
         const long long mirror = (t_out >= 1 && t_out <= c.o_halo) ? row - 2ll * t_out * c.o_st : -1ll;
-        if (c.raw != nullptr) tc_store_planes(c.raw, c.o_plane, c.o_ld, row, mirror, co0, v, false, c.o_halo_zero != 0);
-        if (c.elu != nullptr) tc_store_planes(c.elu, c.o_plane, c.o_ld, row, mirror, co0, v, true, c.o_halo_zero != 0);
+        if (c.raw != nullptr) tc_store_planes<CW>(c.raw, c.o_plane, c.o_ld, row, mirror, co0, v, false, c.o_halo_zero != 0);
+        if (c.elu != nullptr) tc_store_planes<CW>(c.elu, c.o_plane, c.o_ld, row, mirror, co0, v, true, c.o_halo_zero != 0);
     }
 }
 
-// columns [n0, n0+32) = gates (i, f, g, o) of hidden units [n0/4, n0/4 + 8) of utterance b at step c.t_step
-__device__ __forceinline__ void tc_epilogue_lstm(const TcCall& c, int b, int n0, float (&v)[32]) {
+// columns [n0, n0+CW) = gates (i, f, g, o) of hidden units [n0/4, n0/4 + CW/4) of utterance b at step c.t_step
+template <int CW>
+__device__ __forceinline__ void tc_epilogue_lstm(const TcCall& c, int b, int n0, float (&v)[CW]) {
+    constexpr int U = CW / 4;
     const int j0 = n0 >> 2;
     const size_t tb = static_cast<size_t>(c.t_step) * c.Bcap + b;
     const float4* pr = reinterpret_cast<const float4*>(c.pre + tb * (4 * static_cast<size_t>(c.H)) + n0);
-    float4* cp = reinterpret_cast<float4*>(c.cst + static_cast<size_t>(b) * c.H + j0);
-    float cs[8], h[8];
-    {
-        const float4 c0 = cp[0], c1 = cp[1];
-        cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w;
-        cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    float* cp = c.cst + static_cast<size_t>(b) * c.H + j0;
+    float cs[U], h[U];
+#pragma unroll
+    for (int u = 0; u < U; u += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cp + u);
+        cs[u] = c4.x; cs[u + 1] = c4.y; cs[u + 2] = c4.z; cs[u + 3] = c4.w;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < U; ++u) {
         const float4 g = pr[u];
         const float ig = tc_sigmoid(v[4 * u] + g.x), fg = tc_sigmoid(v[4 * u + 1] + g.y);
         const float gg = tanhf(v[4 * u + 2] + g.z), og = tc_sigmoid(v[4 * u + 3] + g.w);
         cs[u] = fg * cs[u] + ig * gg;
         h[u] = og * tanhf(cs[u]);
     }
-    cp[0] = make_float4(cs[0], cs[1], cs[2], cs[3]);
-    cp[1] = make_float4(cs[4], cs[5], cs[6], cs[7]);
-    uint4 hi, lo;
-    tc_split8(h, hi, lo);
-    __nv_bfloat16* hp = c.hseq + (tb + c.Bcap) * c.H + j0;          // slot t+1
-    *reinterpret_cast<uint4*>(hp) = hi;
-    *reinterpret_cast<uint4*>(hp + c.h_plane) = lo;
-    if (c.elu != nullptr) {
-        const float4* sk = reinterpret_cast<const float4*>(c.skip + tb * c.H + j0);
-        const float4 s0 = sk[0], s1 = sk[1];
-        float w[8] = {h[0] + s0.x, h[1] + s0.y, h[2] + s0.z, h[3] + s0.w, h[4] + s1.x, h[5] + s1.y, h[6] + s1.z, h[7] + s1.w};
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = tc_elu(w[u]);
-        tc_split8(w, hi, lo);
-        __nv_bfloat16* op = c.elu + (b * c.o_sb + c.t_step * c.o_st + c.o_off) * c.o_ld + j0;
-        *reinterpret_cast<uint4*>(op) = hi;
-        *reinterpret_cast<uint4*>(op + c.o_plane) = lo;
+    for (int u = 0; u < U; u += 4) *reinterpret_cast<float4*>(cp + u) = make_float4(cs[u], cs[u + 1], cs[u + 2], cs[u + 3]);
+    __nv_bfloat16* hp = c.hseq + (tb + c.Bcap) * c.H + j0;          // slot t+1
+    const float* sk = c.elu != nullptr ? c.skip + tb * c.H + j0 : nullptr;
+    __nv_bfloat16* op = c.elu != nullptr ? c.elu + (b * c.o_sb + c.t_step * c.o_st + c.o_off) * c.o_ld + j0 : nullptr;
+#pragma unroll
+    for (int u = 0; u < U; u += 4) {
+        uint2 hi, lo;
+        tc_split2(h[u], h[u + 1], hi.x, lo.x);
+        tc_split2(h[u + 2], h[u + 3], hi.y, lo.y);
+        *reinterpret_cast<uint2*>(hp + u) = hi;
+        *reinterpret_cast<uint2*>(hp + c.h_plane + u) = lo;
+        if (op != nullptr) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sk + u);
+            tc_split2(tc_elu(h[u] + s4.x), tc_elu(h[u + 1] + s4.y), hi.x, lo.x);
+            tc_split2(tc_elu(h[u + 2] + s4.z), tc_elu(h[u + 3] + s4.w), hi.y, lo.y);
+            *reinterpret_cast<uint2*>(op + u) = hi;
+            *reinterpret_cast<uint2*>(op + c.o_plane + u) = lo;
+        }
     }
 }
 
-template <int BN, int STAGES>
+template <int CW>
+__device__ __forceinline__ void tc_tmem_ld(uint32_t taddr, float (&v)[CW]) {
+    if constexpr (CW == 32) tmem_ld_32x32(taddr, v);
+    else tmem_ld_32x16(taddr, v);
+}
+
+// Persistent: CTA i works on tiles i, i + grid, ... (tile = m-tile * ntiles + n-tile, n fastest so the CTAs that run
+// together share their A rows in L2).  The TMA producer and the MMA issuer run ahead across tile boundaries through the
+// shared-memory ring; the accumulator is double-buffered in TMEM so the 16 epilogue warps drain tile i while tile i+1 is
+// being multiplied.
+template <int BN, int STAGES, int CW>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ TcCall c) {
@@ -202,16 +224,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tfull = empty_bar + STAGES;                  // [2] accumulator ready
+    uint64_t* tempty = tfull + 2;                          // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int ntile = blockIdx.x % c.ntiles;               // n fastest: the CTAs that share an A tile run together
-    const int mtile = blockIdx.x / c.ntiles;
-    const int r0 = c.row_base + mtile * TC_BM;
     const int total_kb = c.total_kb;
+    const int total_tiles = c.mtiles * c.ntiles;
     const int pre = min(total_kb, STAGES);
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -222,15 +244,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], TC_EPI_WARPS);
+        }
         mbar_fence_init();
-        for (int i = 0; i < pre; ++i) {                     // weights never depend on the previous kernel
-            mbar_arrive_expect_tx(&full_bar[i], L::STAGE_BYTES);
-            tma_load_2d(smem + i * L::STAGE_BYTES + 2 * L::A_BYTES, &tmW, &full_bar[i], 0, (ntile * total_kb + i) * 2 * BN);
+        if (static_cast<int>(blockIdx.x) < total_tiles) {   // weights never depend on the previous kernel
+            const int ntile = blockIdx.x % c.ntiles;
+            for (int i = 0; i < pre; ++i) {
+                mbar_arrive_expect_tx(&full_bar[i], L::STAGE_BYTES);
+                tma_load_2d(smem + i * L::STAGE_BYTES + 2 * L::A_BYTES, &tmW, &full_bar[i], 0, (ntile * total_kb + i) * 2 * BN);
+            }
         }
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN);
+        tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -241,81 +269,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             pdl_wait();                                     // the activation planes come from the previous kernel
-            for (int i = 0; i < total_kb; ++i) {
-                const int stage = i % STAGES, use = i / STAGES;
-                uint8_t* a = smem + stage * L::STAGE_BYTES;
-                if (use > 0) {                              // (the first STAGES k-blocks were armed above, with their weights)
-                    mbar_wait(&empty_bar[stage], (use - 1) & 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_2d(a + 2 * L::A_BYTES, &tmW, &full_bar[stage], 0, (ntile * total_kb + i) * 2 * BN);
+            int g = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ntile = tile % c.ntiles, mtile = tile / c.ntiles;
+                const int r0 = c.row_base + mtile * TC_BM;
+                for (int i = 0; i < total_kb; ++i, ++g) {
+                    const int stage = g % STAGES, use = g / STAGES;
+                    uint8_t* a = smem + stage * L::STAGE_BYTES;
+                    if (g >= pre) {                         // (the first `pre` k-blocks were armed above, with their weights)
+                        if (use > 0) mbar_wait(&empty_bar[stage], (use - 1) & 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        tma_load_2d(a + 2 * L::A_BYTES, &tmW, &full_bar[stage], 0, (ntile * total_kb + i) * 2 * BN);
+                    }
+                    const TcTap tp = c.taps[i];
+                    const CUtensorMap* m = tp.src ? &tmA1 : &tmA0;
+                    const int row = r0 - tp.shift;
+                    tma_load_2d(a, m, &full_bar[stage], tp.coff, row);
+                    tma_load_2d(a + L::A_BYTES, m, &full_bar[stage], tp.coff, c.rcap[tp.src] + row);
                 }
-                const TcTap tp = c.taps[i];
-                const CUtensorMap* m = tp.src ? &tmA1 : &tmA0;
-                const int row = r0 - tp.shift;
-                tma_load_2d(a, m, &full_bar[stage], tp.coff, row);
-                tma_load_2d(a + L::A_BYTES, m, &full_bar[stage], tp.coff, c.rcap[tp.src] + row);
             }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_bf16_f32(TC_BM, BN);
-        int stage = 0, phase = 0;
-        for (int i = 0; i < total_kb; ++i) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint64_t ahi = umma_desc_kmajor_sw128(a_addr);
-                const uint64_t alo = umma_desc_kmajor_sw128(a_addr + L::A_BYTES);
-                const uint64_t bhi = umma_desc_kmajor_sw128(a_addr + 2 * L::A_BYTES);
-                const uint64_t blo = umma_desc_kmajor_sw128(a_addr + 2 * L::A_BYTES + L::B_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    umma_bf16(tmem_base, ahi + 2 * k, bhi + 2 * k, idesc, (i | k) != 0);
-                    umma_bf16(tmem_base, alo + 2 * k, bhi + 2 * k, idesc, 1u);
-                    umma_bf16(tmem_base, ahi + 2 * k, blo + 2 * k, idesc, 1u);
-                }
-                umma_commit(&empty_bar[stage]);
-                if (i == total_kb - 1) umma_commit(tmem_full);
+        int g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            if (it >= 2) {                                  // the epilogue warps have drained this accumulator
+                mbar_wait(&tempty[acc], ((it >> 1) - 1) & 1);
+                tc_fence_after();
             }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int i = 0; i < total_kb; ++i, ++g) {
+                const int stage = g % STAGES;
+                mbar_wait(&full_bar[stage], (g / STAGES) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint64_t ahi = umma_desc_kmajor_sw128(a_addr);
+                    const uint64_t alo = umma_desc_kmajor_sw128(a_addr + L::A_BYTES);
+                    const uint64_t bhi = umma_desc_kmajor_sw128(a_addr + 2 * L::A_BYTES);
+                    const uint64_t blo = umma_desc_kmajor_sw128(a_addr + 2 * L::A_BYTES + L::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        umma_bf16(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, (i | k) != 0);
+                        umma_bf16(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, 1u);
+                        umma_bf16(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (i == total_kb - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+            }
         }
     } else {
-        const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int row = r0 + q * 32 + lane;
-        int b, t;
-        bool valid;
-        if (c.mode == TC_MODE_LSTM) {
-            b = row - c.row_base;
-            t = c.t_step;
-            valid = b < c.B;
-        } else {
-            const int qd = row / c.in_div, rm = row - qd * c.in_div;
-            if (c.in_tm) { t = qd - c.in_halo; b = rm; }
-            else { b = qd; t = rm - c.in_halo; }
-            valid = row < c.rows_total && b < c.B && t >= 0 && t < c.T_in;
-        }
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        pdl_wait();                                         // what this epilogue overwrites may still be read upstream
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int ci = half; ci < BN / 32; ci += 2) {
-            float v[32];
-            tmem_ld_32x32(lane_addr + ci * 32, v);
-            const int n0 = ntile * BN + ci * 32;
-            if (valid && n0 < c.Nstore) {
-                if (c.mode == TC_MODE_LSTM) tc_epilogue_lstm(c, b, n0, v);
-                else tc_epilogue_conv(c, b, t, n0, v);
+        const int q = warp & 3;                             // TMEM lane quarter this warp may read
+        const int grp = (warp - 2) >> 2;                    // which column chunks
+        pdl_wait();                                         // what the epilogue overwrites may still be read upstream
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int ntile = tile % c.ntiles, mtile = tile / c.ntiles;
+            const int acc = it & 1;
+            const int row = c.row_base + mtile * TC_BM + q * 32 + lane;
+            int b, t;
+            bool valid;
+            if (c.mode == TC_MODE_LSTM) {
+                b = row - c.row_base;
+                t = c.t_step;
+                valid = b < c.B;
+            } else {
+                const int qd = row / c.in_div, rm = row - qd * c.in_div;
+                if (c.in_tm) { t = qd - c.in_halo; b = rm; }
+                else { b = qd; t = rm - c.in_halo; }
+                valid = row < c.rows_total && b < c.B && t >= 0 && t < c.T_in;
             }
+            mbar_wait(&tfull[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int ci = grp; ci < BN / CW; ci += TC_EPI_WARPS / 4) {
+                float v[CW];
+                tc_tmem_ld<CW>(lane_addr + ci * CW, v);
+                const int n0 = ntile * BN + ci * CW;
+                if (valid && n0 < c.Nstore) {
+                    if (c.mode == TC_MODE_LSTM) tc_epilogue_lstm<CW>(c, b, n0, v);
+                    else tc_epilogue_conv<CW>(c, b, t, n0, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -403,9 +451,13 @@ struct TcCodec {
     int min_T = 8;
     bool profile = false;
     std::vector<std::pair<std::string, float>> prof;
+    struct Dbg { Plane p; const __nv_bfloat16* ptr; int B; };
+    std::map<std::string, Dbg> dbg;      // tensors of the last decoded chunk (debug read-back)
 };
 
 namespace {
+
+inline int tc_num_sms(const TcCodec* tc) { return tc->num_sms; }
 
 int upload_gemm(TcCodec* tc, TcGemm& g, const std::vector<float>& W, const std::vector<float>& bias, int N, int Ktot, int bn_hint) {
     if (Ktot % TC_BK || Ktot / TC_BK > TC_MAX_KB) {
@@ -542,16 +594,17 @@ int build_lstm(TcCodec* tc, TcGemm& g, const HostW& hw, const std::string& wname
     return upload_gemm(tc, g, W, bias, 4 * H, H, bn_hint);
 }
 
-template <int BN, int STAGES>
-int tc_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const TcGemm& g, const TcCall& c, int mtiles, cudaStream_t st) {
+template <int BN, int STAGES, int CW>
+int tc_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const TcGemm& g, const TcCall& c, int num_sms, cudaStream_t st) {
     using L = TcSmem<BN, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        VCB_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        VCB_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
+    const long long tiles = static_cast<long long>(c.mtiles) * c.ntiles;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(mtiles) * g.ntiles, 1, 1);
+    cfg.gridDim = dim3(static_cast<unsigned>(std::min<long long>(tiles, num_sms)), 1, 1);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
@@ -560,24 +613,26 @@ int tc_launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const TcGemm& g, c
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, a0, a1, g.tmW, c));
+    VCB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, CW>, a0, a1, g.tmW, c));
     return 0;
 }
 
-int tc_launch(const CUtensorMap& a0, const CUtensorMap& a1, const TcGemm& g, TcCall& c, int mtiles, cudaStream_t st) {
+int tc_launch(TcCodec* tc, const CUtensorMap& a0, const CUtensorMap& a1, const TcGemm& g, TcCall& c, int mtiles, cudaStream_t st) {
     c.total_kb = g.total_kb;
     c.ntiles = g.ntiles;
+    c.mtiles = mtiles;
     c.bias = g.bias;
     c.up = g.up;
     c.Cout = g.Cout;
     for (int i = 0; i < g.total_kb; ++i) c.taps[i] = g.taps[i];
     if (static_cast<long long>(mtiles) * g.ntiles > 0x7fffffffll) {
-        set_error("codec_tc: grid too large");
+        set_error("codec_tc: too many tiles");
         return -1;
     }
-    if (g.BN == 128) return tc_launch_t<128, 3>(a0, a1, g, c, mtiles, st);
-    if (g.BN == 64) return g.total_kb > 8 ? tc_launch_t<64, 4>(a0, a1, g, c, mtiles, st) : tc_launch_t<64, 2>(a0, a1, g, c, mtiles, st);
-    return tc_launch_t<32, 2>(a0, a1, g, c, mtiles, st);
+    const int sms = tc_num_sms(tc);
+    if (g.BN == 128) return tc_launch_t<128, 3, 32>(a0, a1, g, c, sms, st);
+    if (g.BN == 64) return tc_launch_t<64, 4, 16>(a0, a1, g, c, sms, st);
+    return tc_launch_t<32, 5, 16>(a0, a1, g, c, sms, st);
 }
 
 // A-side tensor map of an activation tensor form (raw / elu): [2 * rcap rows][C]
@@ -625,7 +680,7 @@ Plane make_um(int C, int B, int T, int halo, int halo_zero) {
     p.Tp = T + halo;
     p.halo = halo;
     p.halo_zero = halo_zero;
-    p.rcap = B * p.Tp;
+    p.rcap = std::max(B * p.Tp, TC_BM);               // (a TMA box never taller than its tensor)
     p.sb = p.Tp;
     p.st = 1;
     p.off = halo;
@@ -736,6 +791,15 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
 
     Prof pf{tc, st};
     CUtensorMap mA, mB;
+    tc->dbg.clear();
+    auto note = [&](const std::string& name, const Plane& p, const __nv_bfloat16* ptr) { tc->dbg[name] = TcCodec::Dbg{p, ptr, B}; };
+    note("z", Z, Z.raw);
+    note("u0", U0, U0.elu);
+    if (nl > 0) {
+        note("x0", X0, X0.raw);
+        note("hs0", HS[0], HS[0].raw);
+        if (nl > 1) note("hs1", HS[1], HS[1].raw);
+    }
     // state that the kernels only ever read: zero halos / initial LSTM state
     VCB_CUDA_OK(cudaMemset2DAsync(U0.elu, static_cast<size_t>(U0.Tp) * U0.C * 2, 0, static_cast<size_t>(U0.C) * 2, B, st));
     VCB_CUDA_OK(cudaMemset2DAsync(U0.elu + U0.plane(), static_cast<size_t>(U0.Tp) * U0.C * 2, 0, static_cast<size_t>(U0.C) * 2, B, st));
@@ -768,7 +832,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
             set_out(c, U0, false, true);
         }
         if (plane_map(&mA, Z.raw, Z)) return -1;
-        if (tc_launch(mA, mA, tc->conv_in, c, (Z.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+        if (tc_launch(tc, mA, mA, tc->conv_in, c, (Z.rcap + TC_BM - 1) / TC_BM, st)) return -1;
         ++*launches;
     }
     pf.end();
@@ -789,7 +853,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
             c.f32 = pre;
             c.f_ld = 4 * H; c.f_valid = 4 * H; c.f_sb = 1; c.f_st = Bcap; c.f_off = 0;
             if (plane_map(&mA, in.raw, in)) return -1;
-            if (tc_launch(mA, mA, tc->pre[l], c, (in.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+            if (tc_launch(tc, mA, mA, tc->pre[l], c, (in.rcap + TC_BM - 1) / TC_BM, st)) return -1;
             ++*launches;
         }
         pf.end();
@@ -817,7 +881,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
             for (int t = 0; t < T; ++t) {
                 c.t_step = t;
                 c.row_base = t * Bcap;
-                if (tc_launch(mA, mA, tc->step[l], c, mt, st)) return -1;
+                if (tc_launch(tc, mA, mA, tc->step[l], c, mt, st)) return -1;
             }
             *launches += T;
         }
@@ -834,6 +898,8 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
         Plane X = make_um(cpad(cout), B, t_cur * r, cf.n_residual_layers > 0 ? (kres - 1) : (last_stage ? kout - 1 : 1),
                           cf.n_residual_layers > 0 ? hz : (last_stage ? hz : 1));
         place(X, ar[side], cf.n_residual_layers > 0, true);
+        note("x" + std::to_string(i + 1) + ".elu", X, X.elu);
+        if (X.raw) note("x" + std::to_string(i + 1) + ".raw", X, X.raw);
         pf.begin("convtr");
         {
             TcCall c;
@@ -842,7 +908,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
             c.Nstore = r * cpad(cout);
             set_out(c, X, cf.n_residual_layers > 0, true);
             if (plane_map(&mA, cur.elu, cur)) return -1;
-            if (tc_launch(mA, mA, tc->up[i], c, (cur.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+            if (tc_launch(tc, mA, mA, tc->up[i], c, (cur.rcap + TC_BM - 1) / TC_BM, st)) return -1;
             ++*launches;
         }
         pf.end();
@@ -857,6 +923,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
             Hd.raw = nullptr;
             Hd.halo_zero = 0;
             place(Hd, arh, false, true);
+            note("h" + std::to_string(i + 1) + "." + std::to_string(j), Hd, Hd.elu);
             pf.begin("res_conv1");
             {
                 TcCall c;
@@ -866,7 +933,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
                 set_out(c, Hd, false, true);
                 c.o_halo = 0;
                 if (plane_map(&mA, X.elu, X)) return -1;
-                if (tc_launch(mA, mA, tc->res1[i][j], c, (X.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+                if (tc_launch(tc, mA, mA, tc->res1[i][j], c, (X.rcap + TC_BM - 1) / TC_BM, st)) return -1;
                 ++*launches;
             }
             pf.end();
@@ -876,6 +943,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
             else if (last_stage) O = make_um(cpad(ch), B, t_cur, kout - 1, hz);
             else O = make_um(cpad(ch), B, t_cur, 1, 1);
             place(O, ar[side ^ 1], !last_res, true);
+            note("o" + std::to_string(i + 1) + "." + std::to_string(j), O, O.elu);
             pf.begin("res_conv2");
             {
                 TcCall c;
@@ -885,7 +953,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
                 c.Nstore = cpad(ch);
                 set_out(c, O, !last_res, true);
                 if (plane_map(&mA, Hd.elu, Hd) || plane_map(&mB, X.raw, X)) return -1;
-                if (tc_launch(mA, mB, tc->res2[i][j], c, (X.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+                if (tc_launch(tc, mA, mB, tc->res2[i][j], c, (X.rcap + TC_BM - 1) / TC_BM, st)) return -1;
                 ++*launches;
             }
             pf.end();
@@ -905,7 +973,7 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
         c.f32 = wav;
         c.f_ld = 1; c.f_valid = 1; c.f_scalar = 1; c.f_sb = t_cur; c.f_st = 1; c.f_off = 0;
         if (plane_map(&mA, cur.elu, cur)) return -1;
-        if (tc_launch(mA, mA, tc->conv_out, c, (cur.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+        if (tc_launch(tc, mA, mA, tc->conv_out, c, (cur.rcap + TC_BM - 1) / TC_BM, st)) return -1;
         ++*launches;
     }
     pf.end();
@@ -939,6 +1007,12 @@ int tc_codec_build(const enc_config& cfg, const std::map<std::string, float*>& w
     tc->Dp = cpad(cfg.dimension);
     tc->ch0 = ch0;
     for (int i = 0; i < cfg.n_ratios; ++i) tc->hop *= cfg.ratios[i];
+    {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            tc->num_sms = sms;
+        if (getenv("VCB_CODEC_GRID")) tc->num_sms = std::max(1, atoi(getenv("VCB_CODEC_GRID")));
+    }
     tc->profile = getenv("VCB_CODEC_PROFILE") && atoi(getenv("VCB_CODEC_PROFILE")) != 0;
     const char* lim = getenv("VCB_CODEC_WS_GB");
     tc->ws_limit = static_cast<size_t>((lim ? atof(lim) : 100.0) * (1ull << 30));
@@ -1050,5 +1124,33 @@ void tc_codec_destroy(TcCodec* tc) {
 }
 
 const std::vector<std::pair<std::string, float>>& tc_codec_profile(const TcCodec* c) { return c->prof; }
+
+int tc_codec_debug_tensor(TcCodec* tc, const char* name, float* host_out, int64_t cap, int32_t* dims) {
+    auto it = tc->dbg.find(name);
+    if (it == tc->dbg.end()) {
+        set_error("codec_tc: no tensor '%s' in the last decode", name);
+        return -1;
+    }
+    const Plane& p = it->second.p;
+    const int B = it->second.B;
+    dims[0] = B; dims[1] = p.C; dims[2] = p.Tp; dims[3] = p.halo;
+    const int64_t n = static_cast<int64_t>(B) * p.C * p.Tp;
+    if (host_out == nullptr) return 0;
+    if (cap < n) {
+        set_error("codec_tc: debug buffer too small");
+        return -1;
+    }
+    VCB_CUDA_OK(cudaDeviceSynchronize());
+    std::vector<uint16_t> h(static_cast<size_t>(p.rcap) * p.C * 2);
+    VCB_CUDA_OK(cudaMemcpy(h.data(), it->second.ptr, h.size() * 2, cudaMemcpyDeviceToHost));
+    const size_t pl = static_cast<size_t>(p.plane());
+    for (int b = 0; b < B; ++b)
+        for (int t = -p.halo; t < p.T; ++t) {
+            const long long row = b * p.sb + t * p.st + p.off;
+            for (int ch = 0; ch < p.C; ++ch)
+                host_out[(static_cast<size_t>(b) * p.C + ch) * p.Tp + (t + p.halo)] = bf2f(h[row * p.C + ch]) + bf2f(h[pl + row * p.C + ch]);
+        }
+    return 0;
+}
 
 }  // namespace vcb

@@ -23,4 +23,7 @@ void tc_codec_destroy(TcCodec* c);
 // per-layer device times of the last decode when VCB_CODEC_PROFILE=1 (name, ms), in launch order
 const std::vector<std::pair<std::string, float>>& tc_codec_profile(const TcCodec* c);
 
+// debug: tensor `name` of the last decoded chunk as fp32 [B][C][halo + T] (hi + lo); dims = {B, C, halo + T, halo}
+int tc_codec_debug_tensor(TcCodec* c, const char* name, float* host_out, int64_t cap, int32_t* dims);
+
 }  // namespace vcb

@@ -51,6 +51,7 @@ struct ConvArgs {
     int Cin, Cout, Tin, Tout, ks, dil, padL, reflect, elu_in;
     int convT, r;          // transposed conv: stride r, kernel 2r, one GEMM per phase (blockIdx.z % r)
     int stride;            // forward conv stride (encoder down-sampling: stride r, kernel 2r); 1 in the decoder
+    int Lp;                // reflect padding mirrors a signal of this length (= Tin, or max_pad + 1 zero-extended: audiocraft pad1d)
 };
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
@@ -105,8 +106,14 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvArgs a) {
                         src = n * a.stride + kx * a.dil - a.padL;
                         ok = n < a.Tout;
                         if (ok && (src < 0 || src >= a.Tin)) {
-                            if (a.reflect) src = src < 0 ? -src : 2 * (a.Tin - 1) - src;
-                            else ok = false;
+                            if (a.reflect) {
+                                // audiocraft pad1d: an input no longer than the padding is first zero-extended to Lp samples
+                                if (src < 0) src = -src;
+                                else if (src >= a.Lp) src = 2 * (a.Lp - 1) - src;
+                                ok = src >= 0 && src < a.Tin;
+                            } else {
+                                ok = false;
+                            }
                         }
                     }
                     if (ok) {
@@ -315,6 +322,8 @@ ConvArgs conv_args(const enc_engine* e, const float* A, const float* bias, const
     a.reflect = e->cfg.pad_reflect;
     a.elu_in = elu_in;
     a.stride = 1;
+    const int max_pad = std::max(a.padL, total - a.padL);
+    a.Lp = (a.reflect && T <= max_pad) ? max_pad + 1 : T;
     return a;
 }
 
@@ -327,6 +336,9 @@ ConvArgs conv_args_strided(const enc_engine* e, const float* A, const float* bia
     a.padL = e->cfg.causal ? total : total - total / 2;
     a.stride = stride;
     a.Tout = (Tin + stride - 1) / stride;
+    const int extra = (a.Tout - 1) * stride + ks - total - Tin;    // right padding that completes the last window
+    const int max_pad = std::max(a.padL, total - a.padL + extra);
+    a.Lp = (a.reflect && Tin <= max_pad) ? max_pad + 1 : Tin;
     return a;
 }
 
@@ -498,7 +510,7 @@ int decode_chunk(enc_engine* e, const int64_t* codes, float* wav, int B, int T, 
         ConvArgs a;
         memset(&a, 0, sizeof(a));
         a.A = wt; a.bias = bs; a.in = x; a.out = y;
-        a.Cin = ch; a.Cout = ch / 2; a.Tin = t_cur; a.Tout = t_cur * r; a.convT = 1; a.r = r; a.elu_in = 1; a.stride = 1;
+        a.Cin = ch; a.Cout = ch / 2; a.Tin = t_cur; a.Tout = t_cur * r; a.convT = 1; a.r = r; a.elu_in = 1; a.stride = 1; a.Lp = t_cur;
         const int total = r;                            // kernel 2r - stride r
         const int right = c.causal ? static_cast<int>(ceilf(total * c.trim_right_ratio)) : total / 2;
         a.padL = total - right;                         // samples trimmed on the left
@@ -707,6 +719,14 @@ int enc_encode(enc_engine* e, const float* wav_dev, int64_t* codes_dev, int32_t 
             return -1;
     }
     return 0;
+}
+
+int enc_debug_tensor(enc_engine* e, const char* name, float* host_out, int64_t cap, int32_t* dims) {
+    if (!e || !e->tc) {
+        set_error("codec: the tensor-core decoder is not active (%s)", e ? e->tc_reason : "null engine");
+        return -1;
+    }
+    return tc_codec_debug_tensor(e->tc, name, host_out, cap, dims);
 }
 
 int64_t enc_counter(enc_engine* e, const char* name) {
