@@ -51,6 +51,7 @@ struct TcTap {
 struct TcCall {
     int total_kb, ntiles, mtiles, rows_total, row_base;
     int rcap[2];                       // rows per plane of A source 0 / 1 (lo plane = + rcap rows)
+    int in_store_halo;                 // 1: halo rows (t >= -in_halo) are computed and stored too
     int in_div, in_tm, in_halo, T_in, B;   // A row -> (b, t): utterance-major (row / Tp, row % Tp - halo) or time-major
     int mode, up, Cout, Nstore;        // GEMM column n -> (phase p = n / Cout, channel n % Cout); columns >= Nstore are padding
     const float* bias;
@@ -99,6 +100,13 @@ __device__ __forceinline__ void tc_split8(const float* v, uint4& hi, uint4& lo) 
     tc_split2(v[6], v[7], hi.w, lo.w);
 }
 
+// 32 bytes per lane in one instruction (STG.256, sm_100): every lane writes a whole 32-byte sector
+__device__ __forceinline__ void tc_st256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // CW consecutive channels of one row -> both planes (and the mirrored halo row, if any)
 template <int CW>
 __device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long plane, int ld, long long row, long long mirror,
@@ -111,36 +119,32 @@ __device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long p
         for (int u = 0; u < 8; ++u) w[u] = elu ? tc_elu(v[8 * j + u]) : v[8 * j + u];
         tc_split8(w, hi[j], lo[j]);
     }
-    uint4* ph = reinterpret_cast<uint4*>(base + row * ld + co0);
-    uint4* pl = reinterpret_cast<uint4*>(base + plane + row * ld + co0);
+    __nv_bfloat16* ph = base + row * ld + co0;
+    __nv_bfloat16* pl = ph + plane;
 #pragma unroll
-    for (int j = 0; j < CW / 8; ++j) {
-        ph[j] = hi[j];
-        pl[j] = lo[j];
+    for (int j = 0; j < CW / 16; ++j) {
+        tc_st256(ph + 16 * j, hi[2 * j], hi[2 * j + 1]);
+        tc_st256(pl + 16 * j, lo[2 * j], lo[2 * j + 1]);
     }
     if (mirror >= 0) {
-        uint4* mh = reinterpret_cast<uint4*>(base + mirror * ld + co0);
-        uint4* ml = reinterpret_cast<uint4*>(base + plane + mirror * ld + co0);
+        __nv_bfloat16* mh = base + mirror * ld + co0;
+        __nv_bfloat16* ml = mh + plane;
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-            mh[j] = zero_mirror ? z : hi[j];
-            ml[j] = zero_mirror ? z : lo[j];
+        for (int j = 0; j < CW / 16; ++j) {
+            tc_st256(mh + 16 * j, zero_mirror ? z : hi[2 * j], zero_mirror ? z : hi[2 * j + 1]);
+            tc_st256(ml + 16 * j, zero_mirror ? z : lo[2 * j], zero_mirror ? z : lo[2 * j + 1]);
         }
     }
 }
 
 template <int CW>
-__device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, int n0, float (&v)[CW]) {
+__device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, int n0, float (&v)[CW], const float4 (&bias)[CW / 4]) {
     const int p = n0 / c.Cout, co0 = n0 - p * c.Cout;
     const int t_out = t * c.up + p;
-    {
-        const float4* b4 = reinterpret_cast<const float4*>(c.bias + n0);
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j) {
-            const float4 bb = b4[j];
-            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-        }
+    for (int j = 0; j < CW / 4; ++j) {
+        v[4 * j] += bias[j].x; v[4 * j + 1] += bias[j].y; v[4 * j + 2] += bias[j].z; v[4 * j + 3] += bias[j].w;
     }
     if (c.f32 != nullptr) {
         float* dst = c.f32 + (b * c.f_sb + t_out * c.f_st + c.f_off) * c.f_ld + co0;
@@ -151,7 +155,8 @@ __device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, 
         } else if (co0 < c.f_valid) {
             float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-            for (int j = 0; j < CW / 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CW / 4; ++j)
+                if (co0 + 4 * j < c.f_valid) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
     }
     if (c.raw != nullptr || c.elu != nullptr) {
@@ -340,19 +345,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int qd = row / c.in_div, rm = row - qd * c.in_div;
                 if (c.in_tm) { t = qd - c.in_halo; b = rm; }
                 else { b = qd; t = rm - c.in_halo; }
-                valid = row < c.rows_total && b < c.B && t >= 0 && t < c.T_in;
+                valid = row < c.rows_total && b < c.B && t >= (c.in_store_halo ? -c.in_halo : 0) && t < c.T_in;
+            }
+            // BN / CW <= 4 chunks and 4 warp groups: a warp owns at most one chunk of every tile.  Its bias is fetched while
+            // the accumulator is still being produced.
+            static_assert(BN / CW <= TC_EPI_WARPS / 4, "one column chunk per epilogue warp");
+            const bool has_chunk = grp < BN / CW;
+            const int n0 = ntile * BN + grp * CW;
+            float4 bias[CW / 4];
+            if (has_chunk) {
+                const float4* b4 = reinterpret_cast<const float4*>(c.bias + n0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) bias[j] = b4[j];
             }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t lane_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-            for (int ci = grp; ci < BN / CW; ci += TC_EPI_WARPS / 4) {
+            if (has_chunk) {
                 float v[CW];
-                tc_tmem_ld<CW>(lane_addr + ci * CW, v);
-                const int n0 = ntile * BN + ci * CW;
+                tc_tmem_ld<CW>(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + grp * CW, v);
                 if (valid && n0 < c.Nstore) {
                     if (c.mode == TC_MODE_LSTM) tc_epilogue_lstm<CW>(c, b, n0, v);
-                    else tc_epilogue_conv<CW>(c, b, t, n0, v);
+                    else tc_epilogue_conv<CW>(c, b, t, n0, v, bias);
                 }
             }
             tc_fence_before();
@@ -392,6 +405,33 @@ tc_rvq_planes_kernel(const long long* __restrict__ codes, const float* const* __
             }
         }
     }
+}
+
+// Final convolution (C channels -> 1 channel, k taps), split so that the activation planes are read ONCE:
+//   P[row][j] = sum_c w[c][j] * x[row][c]          one k = 1 GEMM with N = k columns (conv_tc_kernel, fp32 rows of 8)
+//   out[t]    = bias + sum_j P[t - (k-1-j)][j]     this kernel: k shifted diagonals, staged through shared memory
+// (as a k-tap implicit GEMM it would pull k shifted copies of every 128-row tile through shared memory for one output column).
+static constexpr int DS_ROWS = 256;
+static constexpr int DS_LD = 8;                            // floats per P row (k <= 8)
+__global__ void __launch_bounds__(DS_ROWS)
+tc_diag_sum_kernel(const float* __restrict__ P, int k, float bias, float* __restrict__ out, int rows_total, int Tp, int halo,
+                   int T, int B) {
+    __shared__ float ps[(DS_ROWS + DS_LD) * (DS_LD + 1)];
+    const long long r0 = static_cast<long long>(blockIdx.x) * DS_ROWS - (k - 1);
+    pdl_wait();
+    const int W = DS_ROWS + k - 1;
+    for (int i = threadIdx.x; i < W * DS_LD; i += DS_ROWS) {  // contiguous floats of P: coalesced
+        const long long row = r0 + i / DS_LD;
+        ps[(i / DS_LD) * (DS_LD + 1) + (i % DS_LD)] = (row >= 0 && row < rows_total) ? P[row * DS_LD + (i % DS_LD)] : 0.f;
+    }
+    __syncthreads();
+    const long long row = static_cast<long long>(blockIdx.x) * DS_ROWS + threadIdx.x;
+    if (row >= rows_total) return;
+    const int b = static_cast<int>(row / Tp), t = static_cast<int>(row - static_cast<long long>(b) * Tp) - halo;
+    if (b >= B || t < 0 || t >= T) return;
+    float acc = bias;
+    for (int j = 0; j < k; ++j) acc += ps[(threadIdx.x + j) * (DS_LD + 1) + j];   // window row threadIdx.x + j = t - (k-1-j)
+    out[static_cast<size_t>(b) * T + t] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -442,6 +482,9 @@ struct TcCodec {
     int hop = 1, D = 0, Dp = 0, ch0 = 0, num_sms = 148;
     const float** d_embed = nullptr;
     TcGemm conv_in, conv_out;
+    TcGemm conv_out_p;                 // final conv as per-tap partial products (N = k), summed by tc_diag_sum_kernel
+    bool co_split = false;
+    float co_bias = 0.f;
     std::vector<TcGemm> pre, step, up;
     std::vector<std::vector<TcGemm>> res1, res2;
     std::vector<void*> owned;
@@ -466,7 +509,7 @@ int upload_gemm(TcCodec* tc, TcGemm& g, const std::vector<float>& W, const std::
     }
     g.N = N;
     g.total_kb = Ktot / TC_BK;
-    g.BN = bn_hint ? bn_hint : (N >= 128 && g.total_kb > 8 ? 128 : (N >= 64 ? 64 : 32));
+    g.BN = bn_hint ? bn_hint : (N >= 128 ? 128 : (N >= 64 ? 64 : 32));
     g.ntiles = (N + g.BN - 1) / g.BN;
     const int Npad = g.ntiles * g.BN;
     std::vector<uint16_t> t(static_cast<size_t>(Npad) * Ktot * 2);
@@ -781,6 +824,12 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
     ar[0] = static_cast<uint8_t*>(ws.take(arenaX));
     ar[1] = static_cast<uint8_t*>(ws.take(arenaX));
     uint8_t* arh = static_cast<uint8_t*>(ws.take(arenaH));
+    float* copart = nullptr;                                       // per-tap partial products of the final conv
+    if (tc->co_split) {
+        int t = T;
+        for (int i = 0; i < cf.n_ratios; ++i) t *= cf.ratios[i];
+        copart = static_cast<float*>(ws.take((static_cast<size_t>(B) * (t + std::max(kout - 1, 1)) + TC_BM) * DS_LD * 4));
+    }
     if (need) *need = ws.off;
     if (dry) return 0;
     auto place = [&](Plane& p, uint8_t* base, bool raw, bool elu) {
@@ -965,7 +1014,29 @@ int decode_chunk_tc(TcCodec* tc, const int64_t* codes, float* wav, int B, int T,
     }
     // ---- conv_out -> waveform
     pf.begin("conv_out");
-    {
+    if (tc->co_split) {
+        TcCall c;
+        memset(&c, 0, sizeof(c));
+        set_in(c, cur, B);
+        c.in_store_halo = 1;
+        c.Nstore = 16;
+        c.f32 = copart;
+        c.f_ld = DS_LD; c.f_valid = DS_LD; c.f_sb = cur.sb; c.f_st = 1; c.f_off = cur.off;
+        if (plane_map(&mA, cur.elu, cur)) return -1;
+        if (tc_launch(tc, mA, mA, tc->conv_out_p, c, (cur.rcap + TC_BM - 1) / TC_BM, st)) return -1;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((cur.rcap + DS_ROWS - 1) / DS_ROWS);
+        lc.blockDim = dim3(DS_ROWS);
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        VCB_CUDA_OK(cudaLaunchKernelEx(&lc, tc_diag_sum_kernel, static_cast<const float*>(copart), kout, tc->co_bias, wav, cur.rcap,
+                                       cur.Tp, cur.halo, t_cur, B));
+        *launches += 2;
+    } else {
         TcCall c;
         memset(&c, 0, sizeof(c));
         set_in(c, cur, B);
@@ -1070,6 +1141,23 @@ int tc_codec_build(const enc_config& cfg, const std::map<std::string, float*>& w
         }
     }
     if (!rc) rc = build_conv(tc, tc->conv_out, hw, "dec.conv_out", ch, 1, cfg.last_kernel_size, 1, 32);
+    if (!rc && cfg.last_kernel_size <= DS_LD && !(getenv("VCB_CODEC_CONVOUT_TC") && atoi(getenv("VCB_CODEC_CONVOUT_TC")))) {
+        std::vector<float> w, b;
+        rc = hw.get("dec.conv_out.weight", w) || hw.get("dec.conv_out.bias", b) ? -1 : 0;
+        if (!rc) {
+            const int Cp = cpad(ch), k = cfg.last_kernel_size;
+            std::vector<float> W(static_cast<size_t>(k) * Cp, 0.f);          // GEMM row j = tap j
+            for (int ci = 0; ci < ch; ++ci)
+                for (int j = 0; j < k; ++j) W[static_cast<size_t>(j) * Cp + ci] = w[static_cast<size_t>(ci) * k + j];
+            TcGemm& g = tc->conv_out_p;
+            for (int cb = 0; cb < Cp / TC_BK; ++cb) g.taps.push_back(TcTap{0, 0, cb * TC_BK});
+            g.Cout = 32;
+            g.up = 1;
+            rc = upload_gemm(tc, g, W, std::vector<float>(), k, Cp, 32);
+            tc->co_bias = b[0];
+            tc->co_split = rc == 0;
+        }
+    }
     tc->min_T = std::max(tc->min_T, std::max(cfg.kernel_size, cfg.last_kernel_size) + 1);
     if (rc) {
         tc_codec_destroy(tc);
