@@ -9,4 +9,4 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 
 timeout 900 $TR --master-port 29511 bench.py --gpus 2 --no-cpu > $O/bench_tts_2gpu.json 2> $O/bench_tts_2gpu.err
 timeout 900 $TR --master-port 29512 bench.py --gpus 2 --workload edit --no-cpu > $O/bench_edit_2gpu.json 2> $O/bench_edit_2gpu.err
 timeout 600 $TR --master-port 29513 bench.py --gpus 2 --impl reference --steps 4 --warmup 1 > $O/bench_ref_2gpu.json 2> $O/bench_ref_2gpu.err
-head -c 1500 $O/bench_tts_2gpu.json; echo; cat $O/bench_edit_2gpu.json; tail -3 $O/bench_tts_2gpu.err $O/bench_edit_2gpu.err
+head -c 1500 $O/bench_tts_2gpu.json; echo; cat $O/bench_edit_2gpu.json; tail -n 3 $O/bench_tts_2gpu.err; tail -n 3 $O/bench_edit_2gpu.err
