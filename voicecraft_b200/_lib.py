@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvcb200.so")
+LIB_PATH = os.environ.get("VCB_LIB") or os.path.join(_HERE, "libvcb200.so")   # VCB_LIB: A/B runs of two builds
 
 
 class VcbError(RuntimeError):

@@ -81,13 +81,9 @@ struct TcSmem {
     static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
 };
 
-// ELU for the planes the next layer reads: exp through one ex2.approx (absolute error ~2e-7, far below the 2^-17 relative
-// error of the hi/lo split it feeds), branch-free -- the epilogue of the narrow stages is instruction-bound
-__device__ __forceinline__ float tc_elu(float x) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f) * 1.4426950408889634f));
-    return x > 0.f ? x : e - 1.f;
-}
+// ELU for the planes the next layer reads: exp through ex2.approx (absolute error ~2e-7, far below the 2^-17 relative
+// error of the hi/lo split it feeds)
+__device__ __forceinline__ float tc_elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 __device__ __forceinline__ float tc_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 // two fp32 -> packed bf16x2 hi parts and bf16x2 lo parts (same roundings as split_bf16)
@@ -97,54 +93,60 @@ __device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32
     __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+__device__ __forceinline__ void tc_split8(const float* v, uint4& hi, uint4& lo) {
+    tc_split2(v[0], v[1], hi.x, lo.x);
+    tc_split2(v[2], v[3], hi.y, lo.y);
+    tc_split2(v[4], v[5], hi.z, lo.z);
+    tc_split2(v[6], v[7], hi.w, lo.w);
+}
 
 // 32 bytes per lane in one instruction (STG.256, sm_100): every lane writes a whole 32-byte sector
-__device__ __forceinline__ void tc_st256(void* p, const uint32_t* w) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
-                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+__device__ __forceinline__ void tc_st256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                  : "memory");
 }
 
-// CW consecutive channels of one row -> both planes at element offset `off` (and at `moff` for the mirrored halo row, if >= 0);
-// 16 channels (one 32-byte sector per plane) at a time to keep the live registers low
-template <int CW, bool ELU>
-__device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long plane, long long off, long long moff, const float (&v)[CW],
-                                                bool zero_mirror) {
-    __nv_bfloat16* ph = base + off;
+// CW consecutive channels of one row -> both planes (and the mirrored halo row, if any).
+// (Measured and rejected, same box A/B `gpurun_out/r2q`: a branch-free ex2.approx ELU + 16-column chunks everywhere + the bias
+// fetched after the accumulator wait (L1-prefetched) made the narrow stages 20-50 % slower: 147 -> 156 ms at B = 256.)
+template <int CW>
+__device__ __forceinline__ void tc_store_planes(__nv_bfloat16* base, long long plane, int ld, long long row, long long mirror,
+                                                int co0, const float (&v)[CW], bool elu, bool zero_mirror) {
+    uint4 hi[CW / 8], lo[CW / 8];
+#pragma unroll
+    for (int j = 0; j < CW / 8; ++j) {
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = elu ? tc_elu(v[8 * j + u]) : v[8 * j + u];
+        tc_split8(w, hi[j], lo[j]);
+    }
+    __nv_bfloat16* ph = base + row * ld + co0;
     __nv_bfloat16* pl = ph + plane;
 #pragma unroll
-    for (int g = 0; g < CW / 16; ++g) {
-        uint32_t hi[8], lo[8];
+    for (int j = 0; j < CW / 16; ++j) {
+        tc_st256(ph + 16 * j, hi[2 * j], hi[2 * j + 1]);
+        tc_st256(pl + 16 * j, lo[2 * j], lo[2 * j + 1]);
+    }
+    if (mirror >= 0) {
+        __nv_bfloat16* mh = base + mirror * ld + co0;
+        __nv_bfloat16* ml = mh + plane;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (ELU) tc_split2(tc_elu(v[16 * g + 2 * j]), tc_elu(v[16 * g + 2 * j + 1]), hi[j], lo[j]);
-            else tc_split2(v[16 * g + 2 * j], v[16 * g + 2 * j + 1], hi[j], lo[j]);
-        }
-        tc_st256(ph + 16 * g, hi);
-        tc_st256(pl + 16 * g, lo);
-        if (moff >= 0) {                                   // rows 1..pad of an utterance only
-            if (zero_mirror) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) hi[j] = lo[j] = 0u;
-            }
-            tc_st256(base + moff + 16 * g, hi);
-            tc_st256(base + moff + plane + 16 * g, lo);
+        for (int j = 0; j < CW / 16; ++j) {
+            tc_st256(mh + 16 * j, zero_mirror ? z : hi[2 * j], zero_mirror ? z : hi[2 * j + 1]);
+            tc_st256(ml + 16 * j, zero_mirror ? z : lo[2 * j], zero_mirror ? z : lo[2 * j + 1]);
         }
     }
 }
 
 template <int CW>
-__device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, int n0, float (&v)[CW]) {
-    const int p = c.up == 1 ? 0 : n0 / c.Cout;
-    const int co0 = n0 - p * c.Cout;
+__device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, int n0, float (&v)[CW], const float4 (&bias)[CW / 4]) {
+    const int p = n0 / c.Cout, co0 = n0 - p * c.Cout;
     const int t_out = t * c.up + p;
-    {
-        const float4* b4 = reinterpret_cast<const float4*>(c.bias + n0);      // L1 hit: prefetched before the accumulator wait
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j) {
-            const float4 bb = b4[j];
-            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-        }
+    for (int j = 0; j < CW / 4; ++j) {
+        v[4 * j] += bias[j].x; v[4 * j + 1] += bias[j].y; v[4 * j + 2] += bias[j].z; v[4 * j + 3] += bias[j].w;
     }
     if (c.f32 != nullptr) {
         float* dst = c.f32 + (b * c.f_sb + t_out * c.f_st + c.f_off) * c.f_ld + co0;
@@ -161,10 +163,9 @@ __device__ __forceinline__ void tc_epilogue_conv(const TcCall& c, int b, int t, 
     }
     if (c.raw != nullptr || c.elu != nullptr) {
         const long long row = b * c.o_sb + t_out * c.o_st + c.o_off;
-        const long long off = row * c.o_ld + co0;
-        const long long moff = (t_out >= 1 && t_out <= c.o_halo) ? off - 2ll * t_out * c.o_st * c.o_ld : -1ll;
-        if (c.raw != nullptr) tc_store_planes<CW, false>(c.raw, c.o_plane, off, moff, v, c.o_halo_zero != 0);
-        if (c.elu != nullptr) tc_store_planes<CW, true>(c.elu, c.o_plane, off, moff, v, c.o_halo_zero != 0);
+        const long long mirror = (t_out >= 1 && t_out <= c.o_halo) ? row - 2ll * t_out * c.o_st : -1ll;
+        if (c.raw != nullptr) tc_store_planes<CW>(c.raw, c.o_plane, c.o_ld, row, mirror, co0, v, false, c.o_halo_zero != 0);
+        if (c.elu != nullptr) tc_store_planes<CW>(c.elu, c.o_plane, c.o_ld, row, mirror, co0, v, true, c.o_halo_zero != 0);
     }
 }
 
@@ -348,20 +349,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 else { b = qd; t = rm - c.in_halo; }
                 valid = row < c.rows_total && b < c.B && t >= (c.in_store_halo ? -c.in_halo : 0) && t < c.T_in;
             }
-            // column chunks of CW accumulator columns go round-robin over the 4 warp groups (1 or 2 chunks per warp and tile);
-            // the bias lines are pulled into L1 while the accumulator is still being produced
-            for (int ci = grp; ci < BN / CW; ci += TC_EPI_WARPS / 4)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(c.bias + ntile * BN + ci * CW));
+            // BN / CW <= 4 chunks and 4 warp groups: a warp owns at most one chunk of every tile.  Its bias is fetched while
+            // the accumulator is still being produced.
+            static_assert(BN / CW <= TC_EPI_WARPS / 4, "one column chunk per epilogue warp");
+            const bool has_chunk = grp < BN / CW;
+            const int n0 = ntile * BN + grp * CW;
+            float4 bias[CW / 4];
+            if (has_chunk) {
+                const float4* b4 = reinterpret_cast<const float4*>(c.bias + n0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) bias[j] = b4[j];
+            }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int ci = grp; ci < BN / CW; ci += TC_EPI_WARPS / 4) {
-                const int n0 = ntile * BN + ci * CW;
+            if (has_chunk) {
                 float v[CW];
-                tc_tmem_ld<CW>(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + ci * CW, v);
+                tc_tmem_ld<CW>(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + grp * CW, v);
                 if (valid && n0 < c.Nstore) {
                     if (c.mode == TC_MODE_LSTM) tc_epilogue_lstm<CW>(c, b, n0, v);
-                    else tc_epilogue_conv<CW>(c, b, t, n0, v);
+                    else tc_epilogue_conv<CW>(c, b, t, n0, v, bias);
                 }
             }
             tc_fence_before();
@@ -670,7 +676,7 @@ int tc_launch(TcCodec* tc, const CUtensorMap& a0, const CUtensorMap& a1, const T
         return -1;
     }
     const int sms = tc_num_sms(tc);
-    if (g.BN == 128) return tc_launch_t<128, 3, 16>(a0, a1, g, c, sms, st);
+    if (g.BN == 128) return tc_launch_t<128, 3, 32>(a0, a1, g, c, sms, st);
     if (g.BN == 64) return tc_launch_t<64, 4, 16>(a0, a1, g, c, sms, st);
     return tc_launch_t<32, 5, 16>(a0, a1, g, c, sms, st);
 }
