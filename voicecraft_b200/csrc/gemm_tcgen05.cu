@@ -311,7 +311,12 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
                 const int row = c + j;
-                if (R >= 4) {
+                if (S == 1) {
+                    // no split: the partials stay in this CTA -- plain shared stores, handed over by a named barrier
+                    // (a 1-CTA cluster has no peer to st.async to; compute-sanitizer rejects the remote form there)
+                    *reinterpret_cast<float4*>(red + (static_cast<size_t>(ml) << shR) + row) =
+                        make_float4(hi[j] + lo[j], hi[j + 1] + lo[j + 1], hi[j + 2] + lo[j + 2], hi[j + 3] + lo[j + 3]);
+                } else if (R >= 4) {
                     const int owner = row >> shR, rr = row & (R - 1);
                     const uint32_t off = static_cast<uint32_t>((((z << 7) + ml) << shR) + rr) << 2;
                     st_async_f32x4(mapa_u32(red_addr + off, owner), mapa_u32(bar_addr, owner), hi[j] + lo[j],
@@ -330,7 +335,8 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (threadIdx.x == 64) tl_mark(0x140 + ep.mode);
     }
     if (warp >= 2) {
-        mbar_wait_bounded(red_full, 0);                     // all S partials of my rows have landed (async stores counted)
+        if (S == 1) asm volatile("bar.sync 4, %0;" ::"n"(EPI_THREADS) : "memory");   // every epilogue thread stored its partials
+        else mbar_wait_bounded(red_full, 0);                // all S partials of my rows have landed (async stores counted)
         if (threadIdx.x == 64) tl_mark(0x150 + ep.mode);
         // ===== epilogue part 2: fixed-order sum of the S partials of my R rows + fused epilogue =======
         // scratch aliases pipeline stage 0: every TMA write / MMA read of this CTA's stages has retired (tmem_full), and
