@@ -47,7 +47,8 @@ int enc_encode(enc_engine* e, const float* wav_dev, int64_t* codes_dev, int32_t 
 int64_t enc_counter(enc_engine* e, const char* name); /* "launches", "hop", "flops_per_frame", "tc_enabled", "tc_decodes" */
 /* Debug / tests: an intermediate tensor of the last enc_decode on the tensor-core path ("z", "x0", "u0", "x1.raw", "x1.elu",
  * "h1.0", "o1.0", ...), reassembled from its bf16 (hi, lo) planes as fp32 [B][C][halo + T] on the host.  dims = {B, C, halo + T,
- * halo}; host_out == NULL only queries dims. */
+ * halo}; host_out == NULL only queries dims.  The up-sampling stages share two workspace arenas, so after a full decode only
+ * the tensors of the last stage (and "z", "x0", "u0", "hs*") still hold their values: see scripts/codec_tc_debug.py. */
 int enc_debug_tensor(enc_engine* e, const char* name, float* host_out, int64_t cap, int32_t* dims);
 
 #ifdef __cplusplus
