@@ -1,9 +1,9 @@
 #!/bin/bash
 # Evidence run of the final build: full GPU suite, smoke, bench lines (default / reference arm / fp32 KV / persistent kernel /
 # edit), config 1, EnCodec timings, ncu launch list + full captures of the decode-step kernels and of the codec kernels.
-mkdir -p gpurun_out/final2
+mkdir -p gpurun_out/final3
 cd $GRAFT_REPO_ROOT
-O=gpurun_out/final2
+O=gpurun_out/final3
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,temperature.gpu,power.draw --format=csv > $O/gpu.txt 2>&1
 timeout 1500 python -m pytest tests -m gpu -q > $O/tests_gpu.log 2>&1; echo "exit $?" >> $O/tests_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
