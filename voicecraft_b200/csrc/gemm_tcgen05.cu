@@ -90,7 +90,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
 // Fused epilogue for up to 4 token rows of one output feature m.  All loads of the group are issued before the first
 // dependent use (the per-row chains position -> page -> address would otherwise serialise on L2 latency).
 __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0, int nrows, int m, const float (&sum)[4],
-                                                float bias, float (&xnew)[4], int colx = 0) {
+                                                float bias, float (&xnew)[4], int colx = 0, const float* xpre = nullptr) {
     switch (ep.mode) {
         case EPI_QKV: {
             int pos[4], slot[4], page[4];
@@ -127,7 +127,8 @@ __device__ __forceinline__ void apply_epilogue4(const GemmEpilogue& ep, int row0
         case EPI_RESID: {
             float xv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xv[u] = (u < nrows) ? ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] : 0.f;
+            for (int u = 0; u < 4; ++u)
+                xv[u] = xpre ? xpre[u] : ((u < nrows) ? ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m] : 0.f);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 xnew[u] = xv[u] + (sum[u] + bias);
@@ -224,6 +225,9 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // per-feature epilogue constants (bias / LN-fold vector / next gamma) are model weights, never written by a kernel:
     // the epilogue warps fetch them while the mainloop runs, off the critical tail
     float w_bias = 0.f, w_cv = 0.f, w_gnext = 0.f;
+    float e_mean = 0.f, e_rstd = 0.f;                       // LayerNorm statistics of row z*R + lane (BPAD <= 32, see below)
+    float e_x[4] = {0.f, 0.f, 0.f, 0.f};                    // residual rows fetched early (R == 4)
+    bool e_x_valid = false;
     if (warp >= 2) {
         const int m = m0 + (warp & 3) * 32 + lane;
         if (m < Nout) {
@@ -282,6 +286,43 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ml = q * 32 + lane;                       // feature inside the tile
         const int R = BPAD / S;                             // token rows owned by each CTA (power of two)
         const int shR = 31 - __clz(R);
+        // While the mainloop runs: everything the epilogue needs from EARLIER kernels.  With a folded LayerNorm that is the
+        // mean / rstd of my R rows, from the per-tile partial sums the producer kernel left (fixed tile order): lane r of every
+        // warp computes row r (R <= 32 here) and the row groups below fetch it with a shuffle -- no shared memory (the scratch
+        // area aliases a pipeline stage that is still in use now), no barrier, and the L2 round trip is off the critical tail.
+        if constexpr (BPAD <= 32) {
+            pdl_wait();
+            if (ep.ln_fold && lane < R) {
+                const int row = z * R + lane;
+                if (row < nvalid) {
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int t0 = 0; t0 < ep.stats_tiles; t0 += 16) {
+                        float2 v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            v[i] = (t0 + i < ep.stats_tiles)
+                                       ? *reinterpret_cast<const float2*>(ep.stats + (static_cast<size_t>(t0 + i) * STATS_ROWS + row) * 2)
+                                       : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            s1 += v[i].x;
+                            s2 += v[i].y;
+                        }
+                    }
+                    e_mean = s1 * ep.inv_d;
+                    e_rstd = 1.0f / sqrtf(fmaxf(s2 * ep.inv_d - e_mean * e_mean, 0.f) + ep.ln_eps);
+                }
+            }
+            // ... and, when this CTA owns a single group of 4 rows (the out-projection and FFN2 at B = 32: R = 4), the
+            // residual rows it is going to update
+            if (ep.mode == EPI_RESID && R == 4 && m0 + ml < Nout) {
+                const int row0 = z * 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    e_x[u] = (row0 + u < nvalid) ? ep.x[static_cast<size_t>(row0 + u) * ep.ld_out + m0 + ml] : 0.f;
+                e_x_valid = true;
+            }
+        }
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
@@ -353,7 +394,7 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int R = BPAD / S;
         const bool valid_m = m < Nout;
         pdl_wait();                                         // x / stats of earlier kernels are read below
-        if (ep.ln_fold) {
+        if (BPAD > 32 && ep.ln_fold) {
             // mean / rstd of my rows from the per-tile partial sums the producer kernel left (fixed tile order)
             for (int rr = et; rr < R; rr += EPI_THREADS) {
                 const int row = z * R + rr;
@@ -395,11 +436,21 @@ gemm_w_xT_cluster(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 float a = 0.f;
                 if (u < nrows) {
                     for (int zz = 0; zz < S; ++zz) a += red[(zz * GEMM_BM + ml) * R + rr0 + u];
-                    if (ep.ln_fold) a = s_rstd[rr0 + u] * (a - s_mean[rr0 + u] * cv);
+                }
+                if (ep.ln_fold) {
+                    float mean, rstd;
+                    if constexpr (BPAD <= 32) {             // (uniform: every lane of the warp takes part in the shuffle)
+                        mean = __shfl_sync(0xffffffffu, e_mean, (rr0 + u) & 31);
+                        rstd = __shfl_sync(0xffffffffu, e_rstd, (rr0 + u) & 31);
+                    } else {
+                        mean = s_mean[(rr0 + u) & (R - 1)];
+                        rstd = s_rstd[(rr0 + u) & (R - 1)];
+                    }
+                    if (u < nrows) a = rstd * (a - mean * cv);
                 }
                 sum[u] = a;
             }
-            if (valid_m) apply_epilogue4(ep, row0, nrows, m, sum, bias, xnew, colx);
+            if (valid_m) apply_epilogue4(ep, row0, nrows, m, sum, bias, xnew, colx, e_x_valid ? e_x : nullptr);
             if (ep.emit) {
                 // next GEMM's operand gamma_next * x_new (hi/lo) and this tile's (sum x, sum x^2) per row
                 float p1[4], p2[4];

@@ -1575,6 +1575,12 @@ int vcb_bench_gemm(int32_t N, int32_t Kd, int32_t B, int32_t splits, int32_t sta
 int vcb_timeline(int32_t enable, uint64_t* out_host, int32_t max_records, int32_t* n_out) {
     static unsigned long long* buf = nullptr;
     static unsigned int* cnt = nullptr;
+#ifndef VCB_TIMELINE
+    if (enable) {
+        set_error("this libvcb200.so was built without the device timeline marks: rebuild with `make -C voicecraft_b200/csrc clean all TIMELINE=1`");
+        return -1;
+    }
+#endif
     if (enable == 1 || enable == 2) {        // 2: every CTA records its start / wait / end as well
         if (!buf) {
             VCB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&buf), 65536 * 2 * sizeof(unsigned long long)));
