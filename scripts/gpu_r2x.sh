@@ -1,9 +1,9 @@
 #!/bin/bash
 # same-box A/B: LayerNorm statistics fetched by the epilogue warps while the mainloop runs (in-tree build) vs the previous
 # epilogue order (libvcb200_base.so); then the whole GPU suite on the in-tree build
-mkdir -p gpurun_out/r2y
+mkdir -p gpurun_out/r2z
 cd $GRAFT_REPO_ROOT
-O=gpurun_out/r2y
+O=gpurun_out/r2z
 run() { name=$1; shift
   env "$@" timeout 600 python bench.py --no-cpu --no-e2e > $O/bench_$name.json 2>> $O/err.txt
   python - <<PY
