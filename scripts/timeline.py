@@ -1,4 +1,5 @@
-"""Dump a device-side timeline of a few decode steps (830M, B=32) -- which kernels overlap under PDL."""
+"""(needs a library built with the device-timeline marks: `make -C voicecraft_b200/csrc clean all TIMELINE=1`)
+Dump a device-side timeline of a few decode steps (830M, B=32) -- which kernels overlap under PDL."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

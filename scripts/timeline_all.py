@@ -1,4 +1,5 @@
-"""Per-CTA device timeline of one decode step (830M, B=32): for every GEMM / attention launch the spread of CTA start,
+"""(needs a library built with the device-timeline marks: `make -C voicecraft_b200/csrc clean all TIMELINE=1`)
+Per-CTA device timeline of one decode step (830M, B=32): for every GEMM / attention launch the spread of CTA start,
 griddepcontrol.wait return and exit times -- shows launch skew, stragglers and the real inter-kernel gaps."""
 import ctypes as C, os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

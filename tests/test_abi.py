@@ -63,3 +63,18 @@ def test_state_dict_keys_match_reference_layout():
     m.load_state_dict(sd)
     m2 = VoiceCraft(config=vars(cfg))
     assert set(m2.state_dict().keys()) == set(sd.keys())
+
+
+def test_timeline_is_a_build_option():
+    """The device-timeline marks are compiled in only by `make TIMELINE=1` (they cost 2.7 % of a decode step even when
+    disabled): a default build must refuse to start a recording, with a message that says how to get one."""
+    from voicecraft_b200 import _lib
+    lib = _lib.load()
+    rc = lib.vcb_timeline(1, None, 0, None)
+    if rc == 0:                      # a TIMELINE=1 build: stop the recording again
+        import ctypes as C
+        n = C.c_int32(0)
+        lib.vcb_timeline(0, None, 0, C.byref(n))
+        return
+    msg = lib.vcb_last_error()
+    assert b"TIMELINE=1" in msg or b"cuda" in msg.lower(), msg      # (a TIMELINE=1 build on a box without a GPU fails in CUDA)
