@@ -190,3 +190,21 @@ def test_tensor_core_decoder_chunking_is_invisible(monkeypatch):
     tok = _gpu_tok(cfg, sd)
     assert torch.equal(tok.decode_codes(codes), full)
     assert _counter(tok, "tc_decodes") == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_decoder_variants_two_residual_layers_no_lstm(tc, monkeypatch):
+    """Structure variants no fixture covers: two (dilated) residual layers per stage and no LSTM, on the tensor-core path and on
+    the CUDA-core kernels, against the oracle (SNR >= 80 dB / 2e-4 of the peak)."""
+    monkeypatch.setenv("VCB_CODEC_TC", tc)
+    cfg = eo.default_config(n_filters=16, dimension=64, bins=256, n_residual_layers=2, lstm=0)
+    sd = eo.make_state_dict(cfg, seed=21)
+    codes = torch.randint(0, 256, (3, 4, 29), generator=torch.Generator().manual_seed(22))
+    ref = eo.decode(cfg, sd, codes)
+    tok = _gpu_tok(cfg, sd)
+    wav = tok.decode_codes(codes.cuda()).cpu()
+    assert _counter(tok, "tc_enabled") == int(tc)
+    snr = 10 * torch.log10((ref ** 2).sum() / ((wav - ref) ** 2).sum()).item()
+    assert snr >= 80.0, snr
+    assert (wav - ref).abs().max() <= 2e-4 * max(1.0, ref.abs().max().item())
