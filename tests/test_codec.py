@@ -208,3 +208,25 @@ def test_decoder_variants_two_residual_layers_no_lstm(tc, monkeypatch):
     snr = 10 * torch.log10((ref ** 2).sum() / ((wav - ref) ** 2).sum()).item()
     assert snr >= 80.0, snr
     assert (wav - ref).abs().max() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_tensor_core_decoder_is_causal_at_full_length():
+    """Size-independent property at BASELINE's 16 s length (T = 800 frames, 256 000 samples per utterance): the codec is causal,
+    so the waveform of the first 40 frames does not depend on what follows -- bit for bit on the tensor-core path (a row's
+    arithmetic does not depend on the tile it falls in) -- and that prefix is checked against the fp32 oracle."""
+    cfg = eo.default_config()
+    sd = eo.make_state_dict(cfg, seed=31)
+    codes = torch.randint(0, 2048, (2, 4, 800), generator=torch.Generator().manual_seed(32))
+    tok = _gpu_tok(cfg, sd)
+    full = tok.decode_codes(codes.cuda())
+    assert full.shape == (2, 1, 800 * 320) and bool(torch.isfinite(full).all())
+    head = tok.decode_codes(codes[:, :, :40].cuda())
+    assert _counter(tok, "tc_decodes") == 2
+    assert torch.equal(full[..., : 40 * 320], head)
+    ref = eo.decode(cfg, sd, codes[:, :, :40])
+    snr = 10 * torch.log10((ref ** 2).sum() / ((head.cpu() - ref) ** 2).sum()).item()
+    assert snr >= 80.0, snr
+    # the tail is real signal too (not zeros / garbage): its energy is of the order of the head's
+    e_head, e_tail = full[..., : 40 * 320].pow(2).mean().item(), full[..., -40 * 320:].pow(2).mean().item()
+    assert 0.05 * e_head < e_tail < 20.0 * e_head, (e_head, e_tail)
